@@ -1,0 +1,121 @@
+/*
+ * ian_b200.h -- C-ABI of libian_b200.so: the B200-native (sm_100a) implementation of the IAN hot path
+ * of ajbrock/Neural-Photo-Editor.
+ *
+ * The reference has NO native boundary for this path: its contract is the Python class API.IAN
+ * (reference API.py:11-110), whose methods hand numpy arrays to Theano-compiled functions.  Each entry
+ * point below replaces one of those compiled functions; the citation says which.  A host binding
+ * (ctypes, cffi, cgo, JNI ...) needs nothing but this header: plain pointers and sizes, int status
+ * codes, no C++/torch types.  The Python mirror of API.IAN that ships in this repo
+ * (neural-photo-editor_b200/API.py) is such a binding; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns IAN_OK (0) or a negative ian_status; ian_last_error() gives the text.
+ *   - image tensors are float32 NCHW (n,3,64,64) in [-1,1]; latents are float32 (n,100); row-major.
+ *   - *_dev entry points take DEVICE pointers valid on the handle's device and enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = the handle's own stream) without synchronising.
+ *   - *_host entry points take HOST pointers, do H2D, compute, D2H and return after the result landed
+ *     (the numpy-in / numpy-out semantics of the reference's theano.function calls).
+ *   - a handle is bound to one device and is not thread-safe (API.IAN is single-threaded: NPE.py calls
+ *     it from the Tk main loop).
+ */
+#ifndef IAN_B200_H_
+#define IAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ian_handle ian_handle;
+
+typedef enum ian_status {
+  IAN_OK = 0,
+  IAN_ERR_INVALID = -1,   /* bad argument (shape, NULL, non-integral box, empty box ...)        */
+  IAN_ERR_CUDA = -2,      /* CUDA runtime / driver error                                        */
+  IAN_ERR_STATE = -3,     /* call order: parameters missing, not finalized ...                  */
+  IAN_ERR_UNSUPPORTED = -4
+} ian_status;
+
+/* Model graph selector.  Replaces `config_module.get_model(dnn=dnn)` (reference API.py:18-21):
+ * IAN_MODEL_SIMPLE is the graph of reference IAN_simple.py:56-241. */
+typedef enum ian_model_kind { IAN_MODEL_SIMPLE = 0 } ian_model_kind;
+
+/* Compute path of the dense contractions (enc_conv2-4, dec_conv1-3, fully-connected layers).
+ * Both are CUDA on the GPU; there is no CPU path.
+ *   IAN_PATH_TC   : tcgen05 tensor-core kernels, fp32 emulated by a 3-pass bf16 split (default)
+ *   IAN_PATH_SIMT : fp32 FFMA kernels (verification path, bit-for-bit independent of IAN_PATH_TC) */
+typedef enum ian_path { IAN_PATH_TC = 0, IAN_PATH_SIMT = 1 } ian_path;
+
+/* ---- lifecycle: replaces IAN.__init__ (reference API.py:12-64) --------------------------------- */
+
+/* Create an empty model on CUDA device `device`. */
+int ian_create(int model_kind, int device, ian_handle** out);
+
+/* Upload one parameter under its reference checkpoint name ("enc_conv2.W", "bnorm2.inv_std", ...;
+ * names and shapes: reference GANcheckpoints.py:33-57 + IAN_simple.py layer names).  `data` is a HOST
+ * float32 array of `ndim` dims `shape`, in the reference's own layout (conv W (Cout,Cin,5,5); deconv W
+ * (Cin,Cout,5,5); dense W (in,out)).  Unlike the reference loader (which only warns,
+ * GANcheckpoints.py:45-52) an unknown name or a shape mismatch is an error. */
+int ian_set_param(ian_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
+
+/* Check that every parameter of the graph is present, fold BatchNorm (inference), re-lay weights for
+ * the kernels and upload them.  Must precede any compute call. */
+int ian_finalize(ian_handle* h);
+
+int ian_destroy(ian_handle* h);
+const char* ian_last_error(const ian_handle* h);   /* h may be NULL: last error of ian_create     */
+
+int ian_get_zdim(const ian_handle* h);             /* replaces IAN.get_zdim (API.py:92-96) -> 100 */
+int ian_set_path(ian_handle* h, int path);         /* ian_path                                    */
+/* Number of kernels this library launched on the handle since creation (bench.py gpu_launches). */
+int64_t ian_launch_count(const ian_handle* h);
+
+/* ---- encode: replaces Z_hat_fn / IAN.encode_images (reference API.py:50-51, 78-90) ------------- */
+/* z = mu(x) (deterministic=True, what API.py:50 compiles).  If eps != NULL the reparameterised
+ * sample z = mu + exp(logsigma) * eps (reference layers.py:419-433, eps injected: (n,100)).       */
+int ian_encode_dev(ian_handle* h, const float* x, int n, const float* eps, float* z, void* stream);
+int ian_encode_host(ian_handle* h, const float* x, int n, const float* eps, float* z);
+
+/* ---- decode: replaces X_hat_fn / IAN.sample_at (reference API.py:46-47, 98-110) ---------------- */
+int ian_decode_dev(ian_handle* h, const float* z, int n, float* x, void* stream);
+int ian_decode_host(ian_handle* h, const float* z, int n, float* x);
+
+/* ---- encode -> decode in one call (BASELINE metric; no reference equivalent: NPE calls the two
+ * functions back to back, NPE.py:257-261) ------------------------------------------------------- */
+int ian_reconstruct_dev(ian_handle* h, const float* x, int n, float* z_out /*nullable*/, float* x_hat,
+                        void* stream);
+int ian_reconstruct_host(ian_handle* h, const float* x, int n, float* z_out /*nullable*/, float* x_hat);
+
+/* ---- latent-brush gradients: replace calculate_RGB_gradient / calculate_lighten_gradient
+ * (reference API.py:59, 64; IAN.imgrad / IAN.imgradRGB API.py:66-76), batched per sample -------- */
+/* boxes: (n,4) int32 rows [c1,r1,c2,r2], half-open box [r1:r2, c1:c2], 0<=c1<c2<=64, 0<=r1<r2<=64.
+ * target: NULL -> lighten gradient d/dz mean(x_hat[k,:,box_k]);
+ *         target_is_frame=0 -> (n,3) colour per sample, broadcast over the frame;
+ *         target_is_frame=1 -> (n,3,64,64) frames (what NPE passes, NPE.py:205).
+ * g: (n,100) = d/dz_k mean((target_k[:,box_k] - x_hat[k,:,box_k])^2).                              */
+int ian_grad_dev(ian_handle* h, const float* z, const int32_t* boxes, const float* target,
+                 int target_is_frame, int n, float* g, void* stream);
+int ian_grad_host(ian_handle* h, const float* z, const int32_t* boxes, const float* target,
+                  int target_is_frame, int n, float* g);
+
+/* ---- latent edit loop: n_steps of the NPE paint rule (reference NPE.py:199-209) per sample:
+ *        g = grad(z);  z <- z - weight * g * (1 + (c2 - c1))        (all float32)
+ * in place on z (n,100).  `weight` = 0.05 in NPE.py:199.                                          */
+int ian_edit_loop_dev(ian_handle* h, float* z, const int32_t* boxes, const float* target,
+                      int target_is_frame, int n, int n_steps, float weight, void* stream);
+int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const float* target,
+                       int target_is_frame, int n, int n_steps, float weight);
+
+/* ---- measurement helpers ----------------------------------------------------------------------- */
+/* Average device time (ms, CUDA events on the launch stream) of the tap-GEMM kernel of layer
+ * `layer_name` ("enc_conv2", "dec_conv1", ...) over the launches since the last reset; returns <0 if
+ * the layer was never timed.  Timing is enabled with ian_set_layer_timing(h, 1). */
+int ian_set_layer_timing(ian_handle* h, int enable);
+double ian_layer_time_ms(ian_handle* h, const char* layer_name, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAN_B200_H_ */

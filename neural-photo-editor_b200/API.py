@@ -1,0 +1,246 @@
+"""Plat-style model API of the Neural Photo Editor, backed by libian_b200.so (sm_100a CUDA).
+
+Drop-in for the reference `API.py` (reference API.py:11-110): same class name, constructor signature
+and method surface (`encode_images`, `sample_at`, `get_zdim`, `imgrad`, `imgradRGB`, attributes `cfg`,
+`weights_fname`, `model`), so `NPE.py:18  model = IAN(config_path='IAN_simple.py', dnn=True)` and every
+later call in NPE.py work unchanged.  All numerics run in the CUDA library through its C-ABI
+(include/ian_b200.h); this file only marshals numpy arrays.  There is no Theano/Lasagne dependency and
+no CPU fallback.
+
+Extensions beyond the reference surface: `reconstruct`, `encode(..., eps)`,
+batched `grad` / `edit_steps`, and `*_dev` variants taking device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+# cfg of reference IAN_simple.py:33-51 (the config module itself imports lasagne/theano and cannot
+# be executed here; the hot path only reads cfg['num_latents'], API.py:96)
+_SIMPLE_CFG = {
+    'batch_size': 128, 'learning_rate': {0: 0.0002}, 'optimizer': 'Adam', 'beta1': 0.5, 'update_ratio': 1,
+    'decay_rate': 0, 'reg': 1e-5, 'momentum': 0.9, 'shuffle': True, 'dims': (64, 64), 'n_channels': 3,
+    'n_classes': 10, 'batches_per_chunk': 64, 'max_epochs': 250, 'checkpoint_every_nth': 1, 'num_latents': 100,
+    'recon_weight': 3.0, 'feature_weight': 1.0,
+}
+_SIMPLE_MODEL_KEYS = ('l_in', 'l_out', 'l_mu', 'l_ls', 'l_Z', 'l_introspect', 'l_discrim')
+
+
+def _f32(a, ndim, what):
+    """theano.function input filtering for a float32 TensorType: wrong dtype / ndim -> TypeError."""
+    a = np.asarray(a)
+    if a.dtype != np.float32:
+        raise TypeError("%s must be float32 (got %s); the reference's theano function rejects it too" % (what, a.dtype))
+    if a.ndim != ndim:
+        raise TypeError("%s must have %d dimensions (got %d)" % (what, ndim, a.ndim))
+    return np.ascontiguousarray(a)
+
+
+def _int_scalar(v, what):
+    """int32 scalar input: non-integral values are rejected, integral floats accepted (NPE.py:202 passes
+    `coords//4` floats); assumption C.8 in SURVEY.md."""
+    iv = int(v)
+    if iv != v:
+        raise TypeError("%s=%r is not an integral value" % (what, v))
+    return iv
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class IAN:
+    """Generic class for using IAN style models with the NPE (reference API.py:11)."""
+
+    def __init__(self, config_path, dnn=True, weights=None, device=0, path=None):
+        """config_path: path of the reference-style config module ('IAN_simple.py'); the weights are read
+        from config_path[:-3]+'.npz' in GANcheckpoints format (reference API.py:18-30) unless a
+        {name: ndarray} dict is given in `weights`.  `dnn` is accepted for signature compatibility (both
+        reference variants of the graph are numerically the same function, IAN_simple.py:141-223)."""
+        base = os.path.basename(str(config_path))
+        if base != 'IAN_simple.py':
+            raise NotImplementedError("config %r: only the IAN_simple graph is built so far" % base)
+        self.cfg = dict(_SIMPLE_CFG)
+        self.weights_fname = str(config_path)[:-3] + '.npz'
+        self.model = {k: 'IAN_simple.' + k for k in _SIMPLE_MODEL_KEYS}
+        self.dnn = dnn
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.ian_create(_lib.IAN_MODEL_SIMPLE, int(device), C.byref(self._h))
+        if rc != _lib.IAN_OK:
+            msg = self._lib.ian_last_error(None)
+            self._h = None
+            raise _lib.IanError("ian_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        print('Loading weights')
+        if weights is None:
+            weights = np.load(self.weights_fname, allow_pickle=False)
+        for name in weights.keys() if hasattr(weights, 'keys') else weights:
+            if name == 'metadata':
+                continue
+            arr = np.ascontiguousarray(np.asarray(weights[name], dtype=np.float32))
+            if name.startswith('minibatch_discrim.') or name.startswith('discrimi.'):
+                continue   # discriminator head: not on the hot path (IAN_simple.py:225-231)
+            shape = (C.c_int64 * arr.ndim)(*arr.shape)
+            self._check(self._lib.ian_set_param(self._h, name.encode(), _fp(arr), shape, arr.ndim))
+        self._check(self._lib.ian_finalize(self._h))
+        if path is not None:
+            self.set_path(path)
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        _lib.check(self._lib, self._h, rc)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.ian_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_path(self, path):
+        """'tc' (tcgen05, default) or 'simt' (fp32 FFMA verification path); both are CUDA."""
+        self._check(self._lib.ian_set_path(self._h, {'tc': _lib.IAN_PATH_TC, 'simt': _lib.IAN_PATH_SIMT}[path]))
+
+    def launch_count(self):
+        return int(self._lib.ian_launch_count(self._h))
+
+    def set_layer_timing(self, enable):
+        self._check(self._lib.ian_set_layer_timing(self._h, int(bool(enable))))
+
+    def layer_time_ms(self, layer, reset=True):
+        return float(self._lib.ian_layer_time_ms(self._h, layer.encode(), int(reset)))
+
+    # ---- reference surface ------------------------------------------------------------------------
+    def imgrad(self, c1, r1, c2, r2, z):
+        """Change in latents which would lighten the local image patch (reference API.py:66-70)."""
+        return self._imgrad(c1, r1, c2, r2, None, z)
+
+    def imgradRGB(self, c1, r1, c2, r2, RGB, z):
+        """Change in latents which would move the local patch towards RGB (reference API.py:72-76)."""
+        return self._imgrad(c1, r1, c2, r2, RGB, z)
+
+    def _imgrad(self, c1, r1, c2, r2, RGB, z):
+        c1, r1, c2, r2 = (_int_scalar(v, n) for v, n in zip((c1, r1, c2, r2), ('c1', 'r1', 'c2', 'r2')))
+        z = _f32(z, 2, 'z')
+        out = np.zeros_like(z)        # only sample 0 is differentiated (API.py:59,64)
+        if z.shape[0] == 0:
+            return out
+        # numpy/theano slice semantics of X_hat[0,:,r1:r2,c1:c2]
+        ra, rb, _ = slice(r1, r2).indices(64)
+        ca, cb, _ = slice(c1, c2).indices(64)
+        if rb <= ra or cb <= ca:
+            out[0] = np.nan           # mean over an empty slice (cannot occur from NPE.py:149)
+            return out
+        boxes = np.array([[ca, ra, cb, rb]], dtype=np.int32)
+        tgt = None
+        if RGB is not None:
+            RGB = _f32(RGB, 4, 'RGB')
+            tgt = np.ascontiguousarray(RGB[0:1])
+            if tgt.shape != (1, 3, 64, 64):
+                raise TypeError("RGB must be (>=1,3,64,64), got %r" % (RGB.shape,))
+        g = np.empty((1, z.shape[1]), np.float32)
+        self._check(self._lib.ian_grad_host(self._h, _fp(np.ascontiguousarray(z[0:1])),
+                                            boxes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            _fp(tgt) if tgt is not None else None, 1, 1, _fp(g)))
+        out[0] = g[0]
+        return out
+
+    def encode_images(self, images):
+        """Encode images x => z: (n,3,s,s) float32 in [-1,1] -> (n, zdim) (reference API.py:78-90)."""
+        return self.encode(images)
+
+    def get_zdim(self):
+        """Integer dimension of the latent z space (reference API.py:92-96)."""
+        return self.cfg['num_latents']
+
+    def sample_at(self, z):
+        """Decode images z => x: (n, zdim) float32 -> (n,3,s,s) in [-1,1] (reference API.py:98-110)."""
+        z = _f32(z, 2, 'z')
+        if z.shape[1] != 100:
+            raise ValueError("z must be (n,100), got %r" % (z.shape,))
+        x = np.empty((z.shape[0], 3, 64, 64), np.float32)
+        if z.shape[0]:
+            self._check(self._lib.ian_decode_host(self._h, _fp(z), z.shape[0], _fp(x)))
+        return x
+
+    # ---- extensions (batched / reparameterised / fused) ------------------------------------------
+    def encode(self, images, eps=None):
+        """deterministic (eps=None): mu(x).  With eps (n,100): mu + exp(logsigma)*eps (layers.py:419-433)."""
+        x = _f32(images, 4, 'images')
+        if x.shape[1:] != (3, 64, 64):
+            raise ValueError("images must be (n,3,64,64), got %r" % (x.shape,))
+        n = x.shape[0]
+        z = np.empty((n, 100), np.float32)
+        if n:
+            e = None if eps is None else _f32(eps, 2, 'eps')
+            self._check(self._lib.ian_encode_host(self._h, _fp(x), n, _fp(e) if e is not None else None, _fp(z)))
+        return z
+
+    def reconstruct(self, images, return_z=False):
+        """encode -> decode in one library call (the BASELINE metric's path)."""
+        x = _f32(images, 4, 'images')
+        n = x.shape[0]
+        xh = np.empty_like(x)
+        z = np.empty((n, 100), np.float32)
+        if n:
+            self._check(self._lib.ian_reconstruct_host(self._h, _fp(x), n, _fp(z), _fp(xh)))
+        return (xh, z) if return_z else xh
+
+    def _target(self, rgb, n):
+        if rgb is None:
+            return None, 0
+        rgb = _f32(rgb, np.asarray(rgb).ndim, 'rgb')
+        if rgb.shape == (n, 3):
+            return rgb, 0
+        if rgb.shape == (n, 3, 64, 64):
+            return rgb, 1
+        raise ValueError("rgb must be (n,3) or (n,3,64,64), got %r" % (rgb.shape,))
+
+    def grad(self, z, boxes, rgb=None):
+        """Per-sample brush gradient: boxes (n,4) int32 [c1,r1,c2,r2]; rgb None (lighten), (n,3) or frames."""
+        z = _f32(z, 2, 'z')
+        n = z.shape[0]
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(n, 4))
+        t, is_frame = self._target(rgb, n)
+        g = np.empty_like(z)
+        self._check(self._lib.ian_grad_host(self._h, _fp(z), boxes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            _fp(t) if t is not None else None, is_frame, n, _fp(g)))
+        return g
+
+    def edit_steps(self, z, boxes, rgb=None, n_steps=32, weight=0.05):
+        """n_steps of the NPE paint rule per sample: Z <- Z - weight*g*(1+(x2-x1)) (reference NPE.py:199-209)."""
+        z = _f32(z, 2, 'z').copy()
+        n = z.shape[0]
+        boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(n, 4))
+        t, is_frame = self._target(rgb, n)
+        self._check(self._lib.ian_edit_loop_host(self._h, _fp(z), boxes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 _fp(t) if t is not None else None, is_frame, n, int(n_steps),
+                                                 float(weight)))
+        return z
+
+    # ---- device-pointer variants (ints from torch.Tensor.data_ptr(); no host copies, async) ----------
+    def reconstruct_dev(self, x_ptr, n, z_ptr, xhat_ptr, stream=0):
+        self._check(self._lib.ian_reconstruct_dev(self._h, x_ptr, n, z_ptr or None, xhat_ptr, stream or None))
+
+    def encode_dev(self, x_ptr, n, z_ptr, eps_ptr=0, stream=0):
+        self._check(self._lib.ian_encode_dev(self._h, x_ptr, n, eps_ptr or None, z_ptr, stream or None))
+
+    def decode_dev(self, z_ptr, n, x_ptr, stream=0):
+        self._check(self._lib.ian_decode_dev(self._h, z_ptr, n, x_ptr, stream or None))
+
+    def grad_dev(self, z_ptr, boxes_ptr, target_ptr, target_is_frame, n, g_ptr, stream=0):
+        self._check(self._lib.ian_grad_dev(self._h, z_ptr, boxes_ptr, target_ptr or None, int(target_is_frame), n,
+                                           g_ptr, stream or None))
+
+    def edit_loop_dev(self, z_ptr, boxes_ptr, target_ptr, target_is_frame, n, n_steps, weight, stream=0):
+        self._check(self._lib.ian_edit_loop_dev(self._h, z_ptr, boxes_ptr, target_ptr or None, int(target_is_frame),
+                                                n, int(n_steps), float(weight), stream or None))

@@ -1,0 +1,18 @@
+// edge.h -- launchers of the HBM-bound end kernels and glue (see edge_kernels.cu).
+#pragma once
+#include "tapgemm.h"
+
+namespace ian {
+// every launcher returns the number of kernels launched (1) or <0 on a launch error
+int launch_conv1(const float* x, const float* wt, const float* bias, __nv_bfloat16* out, long long plane, int n,
+                 cudaStream_t st);
+int launch_dec_out(const __nv_bfloat16* h3, long long plane, const float* wt, float* xhat, int n, cudaStream_t st);
+int launch_sample(const float* head, const float* eps, float* z, __nv_bfloat16* zp, long long zplane, int n,
+                  cudaStream_t st);
+int launch_z_to_planes(const float* z, __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st);
+int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* target, int target_is_frame,
+                          const float* wt, const float* scale3, const __nv_bfloat16* h3, __nv_bfloat16* d3,
+                          long long plane, int n, cudaStream_t st);
+int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
+                        __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st);
+}  // namespace ian

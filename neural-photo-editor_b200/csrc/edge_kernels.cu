@@ -1,0 +1,331 @@
+// edge_kernels.cu -- the HBM-bound ends of the IAN graph and the small glue kernels.
+//   conv1   : enc_conv1  3->128 ch 5x5 s2 + bias + LeakyReLU  (reference IAN_simple.py:73-83)
+//   dec_out : dec_out    128->3 ch 5x5 s2 transposed conv + tanh (IAN_simple.py:171-181, layers.py:436-483)
+//   latent  : GaussianSampleLayer (layers.py:419-433) and float32 <-> split-plane conversion of z
+//   brush   : loss seed (API.py:59,64) fused with dec_out's backward-data and the bnorm_dc3*ReLU mask,
+//             and the NPE step rule (NPE.py:199-209)
+// These have K<=75 or N<=3: no tensor-core shape exists for them, they are written as FFMA kernels
+// with smem-staged weights, vectorised channel-contiguous global access and one fused pass.
+#include "edge.h"
+
+namespace ian {
+
+namespace {
+
+__device__ __forceinline__ float lrelu02(float v) { return 0.6f * v + 0.4f * fabsf(v); }
+
+// ------------------------------------------------------------------------------------------------
+// conv1: x (n,3,64,64) fp32 NCHW -> out (n,32,32,128) split planes.
+// block = one image x 8x8 output pixels; 256 threads = 32 groups of 4 output channels x 8 rows;
+// a thread computes 8 pixels (one tile row) x 4 channels.  Weights [75][128] fp32 in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int C1_TILE = 8;
+constexpr int C1_PATCH = 2 * C1_TILE + 3;   // 19
+
+__global__ void __launch_bounds__(256) conv1_kernel(const float* __restrict__ x, const float* __restrict__ wt /*[75][128]*/,
+                                                    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
+                                                    long long out_plane, int n_img) {
+  __shared__ __align__(16) float Ws[75 * 128];
+  __shared__ float Xs[3][C1_PATCH][C1_PATCH + 1];
+  const int tid = threadIdx.x;
+  const int tiles = 32 / C1_TILE;                 // 4 x 4 tiles per image
+  const int img = blockIdx.x / (tiles * tiles);
+  const int trow = (blockIdx.x / tiles) % tiles, tcol = blockIdx.x % tiles;
+  const int oy0 = trow * C1_TILE, ox0 = tcol * C1_TILE;
+
+  for (int i = tid; i < 75 * 128 / 4; i += 256)
+    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(wt)[i];
+  for (int i = tid; i < 3 * C1_PATCH * C1_PATCH; i += 256) {
+    int c = i / (C1_PATCH * C1_PATCH), r = (i / C1_PATCH) % C1_PATCH, cc = i % C1_PATCH;
+    int iy = 2 * oy0 - 2 + r, ix = 2 * ox0 - 2 + cc;
+    float v = 0.f;
+    if (iy >= 0 && iy < 64 && ix >= 0 && ix < 64) v = x[((long long)(img * 3 + c) * 64 + iy) * 64 + ix];
+    Xs[c][r][cc] = v;
+  }
+  __syncthreads();
+
+  const int cg = tid & 31;        // channel group: channels 4*cg .. 4*cg+3
+  const int py = tid >> 5;        // tile row 0..7
+  float acc[C1_TILE][4];
+#pragma unroll
+  for (int p = 0; p < C1_TILE; ++p)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[p][j] = 0.f;
+
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      float xr[C1_PATCH];
+#pragma unroll
+      for (int k = 0; k < C1_PATCH; ++k) xr[k] = Xs[c][2 * py + i][k];   // warp-uniform: broadcast
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&Ws[((c * 5 + i) * 5 + j) * 128 + cg * 4]);
+#pragma unroll
+        for (int p = 0; p < C1_TILE; ++p) {
+          const float xv = xr[2 * p + j];
+          acc[p][0] = fmaf(xv, w4.x, acc[p][0]);
+          acc[p][1] = fmaf(xv, w4.y, acc[p][1]);
+          acc[p][2] = fmaf(xv, w4.z, acc[p][2]);
+          acc[p][3] = fmaf(xv, w4.w, acc[p][3]);
+        }
+      }
+    }
+  }
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + cg * 4);
+  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+  for (int p = 0; p < C1_TILE; ++p) {
+    const long long pix = (long long)(img * 32 + oy0 + py) * 32 + ox0 + p;
+    __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(lrelu02(acc[p][j] + bb[j]), hi4[j], lo4[j]);
+    *reinterpret_cast<uint2*>(out + pix * 128 + cg * 4) = *reinterpret_cast<uint2*>(hi4);
+    *reinterpret_cast<uint2*>(out + out_plane + pix * 128 + cg * 4) = *reinterpret_cast<uint2*>(lo4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dec_out: h3 (n,32,32,128) split planes -> x_hat (n,3,64,64) fp32 NCHW, tanh.
+//   y[co, 2p+r, 2q+s] = sum_{d,e,ci} h3[p+d, q+e, ci] * W[ci][co][2+2d-r][2+2e-s]
+// block = one image x 8x8 input pixels (-> 16x16 output pixels); warp w handles output phase
+// (r,s) = (w>>1 & 1 ... ) so weight reads are warp-uniform broadcasts.
+// smem: patch [10*10][128+4] fp32 (joined hi+lo), weights [25][128][4] fp32 (co padded to 4).
+// ------------------------------------------------------------------------------------------------
+constexpr int DO_T = 8, DO_P = DO_T + 2, DO_LD = 132;
+
+__global__ void __launch_bounds__(256) dec_out_kernel(const __nv_bfloat16* __restrict__ h3, long long plane,
+                                                      const float* __restrict__ wt /*[25][128][4]*/,
+                                                      float* __restrict__ xhat, int n_img) {
+  extern __shared__ __align__(16) float smem[];
+  float* Xs = smem;                          // [100][132]
+  float* Ws = smem + DO_P * DO_P * DO_LD;    // [25*128*4]
+  const int tid = threadIdx.x;
+  const int img = blockIdx.x >> 4;
+  const int py0 = ((blockIdx.x >> 2) & 3) * DO_T, px0 = (blockIdx.x & 3) * DO_T;
+
+  for (int i = tid; i < 25 * 128; i += 256)
+    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(wt)[i];
+  // patch: 100 pixels x 128 channels, 4 channels per thread-iteration
+  for (int i = tid; i < DO_P * DO_P * 32; i += 256) {
+    const int pix = i >> 5, c4 = (i & 31) * 4;
+    const int iy = py0 - 1 + pix / DO_P, ix = px0 - 1 + pix % DO_P;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < 32 && ix >= 0 && ix < 32) {
+      const __nv_bfloat16* src = h3 + ((long long)(img * 32 + iy) * 32 + ix) * 128 + c4;
+      uint2 h = *reinterpret_cast<const uint2*>(src);
+      uint2 l = *reinterpret_cast<const uint2*>(src + plane);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+      const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+      float2 h0 = __bfloat1622float2(hp[0]), h1 = __bfloat1622float2(hp[1]);
+      float2 l0 = __bfloat1622float2(lp[0]), l1 = __bfloat1622float2(lp[1]);
+      v = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+    }
+    *reinterpret_cast<float4*>(&Xs[pix * DO_LD + c4]) = v;
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int r = (warp >> 1) & 1, s = warp & 1;          // output phase of this warp
+  const int half = warp >> 2;                           // which 32 of the 64 input pixels
+  const int ip = half * 32 + lane;                      // input pixel 0..63
+  const int p = ip >> 3, q = ip & 7;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  // r=0: d in {-1,0,1} -> k = 2+2d ; r=1: d in {0,1} -> k = 1+2d
+  const int dlo_r = r ? 0 : -1, dlo_s = s ? 0 : -1;
+  for (int d = dlo_r; d <= 1; ++d) {
+    const int ki = 2 + 2 * d - r;
+    for (int e = dlo_s; e <= 1; ++e) {
+      const int kj = 2 + 2 * e - s;
+      const float* xp = &Xs[((p + d + 1) * DO_P + (q + e + 1)) * DO_LD];
+      const float* wp = &Ws[(ki * 5 + kj) * 128 * 4];
+#pragma unroll 8
+      for (int ci = 0; ci < 128; ci += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xp + ci);
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + (ci + 0) * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + (ci + 1) * 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(wp + (ci + 2) * 4);
+        const float4 w3 = *reinterpret_cast<const float4*>(wp + (ci + 3) * 4);
+        a0 = fmaf(xv.x, w0.x, a0); a1 = fmaf(xv.x, w0.y, a1); a2 = fmaf(xv.x, w0.z, a2);
+        a0 = fmaf(xv.y, w1.x, a0); a1 = fmaf(xv.y, w1.y, a1); a2 = fmaf(xv.y, w1.z, a2);
+        a0 = fmaf(xv.z, w2.x, a0); a1 = fmaf(xv.z, w2.y, a1); a2 = fmaf(xv.z, w2.z, a2);
+        a0 = fmaf(xv.w, w3.x, a0); a1 = fmaf(xv.w, w3.y, a1); a2 = fmaf(xv.w, w3.z, a2);
+      }
+    }
+  }
+  const int oy = 2 * (py0 + p) + r, ox = 2 * (px0 + q) + s;
+  float* o = xhat + (long long)img * 3 * 4096 + oy * 64 + ox;
+  o[0] = tanhf(a0);
+  o[4096] = tanhf(a1);
+  o[8192] = tanhf(a2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// latent glue
+// ------------------------------------------------------------------------------------------------
+// head (n,256) fp32: mu at [0,100), logsigma at [100,200) -> z fp32 (n,100) and split planes (n,128)
+__global__ void sample_kernel(const float* __restrict__ head, const float* __restrict__ eps, float* __restrict__ z,
+                              __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 128) return;
+  const int k = i / 128, j = i % 128;
+  float v = 0.f;
+  if (j < 100) {
+    v = head[k * 256 + j];
+    if (eps) v = fmaf(expf(head[k * 256 + 100 + j]), eps[k * 100 + j], v);
+    if (z) z[k * 100 + j] = v;
+  }
+  if (zp) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    zp[i] = hi;
+    zp[zplane + i] = lo;
+  }
+}
+
+// z fp32 (n,100) -> split planes (n,128), zero padded
+__global__ void z_to_planes_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 128) return;
+  const int k = i / 128, j = i % 128;
+  const float v = j < 100 ? z[k * 100 + j] : 0.f;
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  zp[i] = hi;
+  zp[zplane + i] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// brush: loss seed + dec_out backward-data + bnorm_dc3 scale * ReLU mask, fused.
+//   seed[k,co,u,v] = coef * (x_hat - t) * (1 - x_hat^2)  inside box_k (coef = 2/(3*bh*bw)), or
+//                    (1/(3*bh*bw)) * (1 - x_hat^2) for the lighten gradient           (API.py:59,64)
+//   d3[k,a,b,ci]   = scale3[ci] * (h3[k,a,b,ci] > 0) * sum_{co,ki,kj} seed[k,co,2+2a-ki,2+2b-kj] * W[ci][co][ki][kj]
+// one thread per (k, a, b, 4 channels); pixels out of reach of the box write zeros.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) brush_seed_bwd_kernel(const float* __restrict__ xhat, const int32_t* __restrict__ boxes,
+                                                             const float* __restrict__ target, int target_is_frame,
+                                                             const float* __restrict__ wt /*[25][128][4]*/,
+                                                             const float* __restrict__ scale3,
+                                                             const __nv_bfloat16* __restrict__ h3,
+                                                             __nv_bfloat16* __restrict__ d3, long long plane, int n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * 1024 * 32) return;
+  const int c4 = (int)(idx & 31) * 4;
+  const long long pix = idx >> 5;
+  const int b = (int)(pix & 31), a = (int)((pix >> 5) & 31), k = (int)(pix >> 10);
+  const int c1 = boxes[k * 4 + 0], r1 = boxes[k * 4 + 1], c2 = boxes[k * 4 + 2], r2 = boxes[k * 4 + 3];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // rows u = 2+2a-ki, ki in 0..4  ->  u in [2a-2, 2a+2]
+  if (2 * a + 2 >= r1 && 2 * a - 2 < r2 && 2 * b + 2 >= c1 && 2 * b - 2 < c2) {
+    const float inv = 1.f / (3.f * (float)(r2 - r1) * (float)(c2 - c1));
+    for (int ki = 0; ki < 5; ++ki) {
+      const int u = 2 + 2 * a - ki;
+      if (u < r1 || u >= r2) continue;
+      for (int kj = 0; kj < 5; ++kj) {
+        const int v = 2 + 2 * b - kj;
+        if (v < c1 || v >= c2) continue;
+        const float* wp = wt + ((ki * 5 + kj) * 128 + c4) * 4;
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+          const float xv = xhat[((long long)(k * 3 + co) * 64 + u) * 64 + v];
+          float sd;
+          if (target) {
+            const float t = target_is_frame ? target[((long long)(k * 3 + co) * 64 + u) * 64 + v] : target[k * 3 + co];
+            sd = 2.f * inv * (xv - t);
+          } else {
+            sd = inv;
+          }
+          sd *= (1.f - xv * xv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(sd, wp[j * 4 + co], acc[j]);
+        }
+      }
+    }
+  }
+  __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+  const long long off = pix * 128 + c4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float mk = __bfloat162float(h3[off + j]);
+    const float v = mk > 0.f ? acc[j] * scale3[c4 + j] : 0.f;
+    split_bf16(v, hi4[j], lo4[j]);
+  }
+  *reinterpret_cast<uint2*>(d3 + off) = *reinterpret_cast<uint2*>(hi4);
+  *reinterpret_cast<uint2*>(d3 + plane + off) = *reinterpret_cast<uint2*>(lo4);
+}
+
+// g fp32 (n,128 padded) -> user g (n,100) and/or z update  z <- z - weight*g*(1+c2-c1)  (NPE.py:206-209)
+__global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_t* __restrict__ boxes, float weight,
+                                    float* __restrict__ g_out, float* __restrict__ z, __nv_bfloat16* __restrict__ zp,
+                                    long long zplane, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 128) return;
+  const int k = i / 128, j = i % 128;
+  float zv = 0.f;
+  if (j < 100) {
+    const float gv = gpad[i];
+    if (g_out) g_out[k * 100 + j] = gv;
+    if (z) {
+      const float fac = 1.f + (float)(boxes[k * 4 + 2] - boxes[k * 4 + 0]);
+      const float grad = gv * fac;                       // NPE.py:206  grad = temp*(1+(x2-x1))
+      zv = z[k * 100 + j] - weight * grad;               // NPE.py:209  Z -= weight*grad
+      z[k * 100 + j] = zv;
+    }
+  }
+  if (z && zp) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(zv, hi, lo);
+    zp[i] = hi;
+    zp[zplane + i] = lo;
+  }
+}
+
+}  // namespace
+
+#define CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 1 : -1)
+
+int launch_conv1(const float* x, const float* wt, const float* bias, __nv_bfloat16* out, long long plane, int n,
+                 cudaStream_t st) {
+  conv1_kernel<<<n * 16, 256, 0, st>>>(x, wt, bias, out, plane, n);
+  return CHECK_LAUNCH();
+}
+
+int dec_out_smem_bytes() { return (DO_P * DO_P * DO_LD + 25 * 128 * 4) * (int)sizeof(float); }
+
+int launch_dec_out(const __nv_bfloat16* h3, long long plane, const float* wt, float* xhat, int n, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(dec_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_out_smem_bytes());
+    attr_set = true;
+  }
+  dec_out_kernel<<<n * 16, 256, dec_out_smem_bytes(), st>>>(h3, plane, wt, xhat, n);
+  return CHECK_LAUNCH();
+}
+
+int launch_sample(const float* head, const float* eps, float* z, __nv_bfloat16* zp, long long zplane, int n,
+                  cudaStream_t st) {
+  sample_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(head, eps, z, zp, zplane, n);
+  return CHECK_LAUNCH();
+}
+
+int launch_z_to_planes(const float* z, __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st) {
+  z_to_planes_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(z, zp, zplane, n);
+  return CHECK_LAUNCH();
+}
+
+int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* target, int target_is_frame,
+                          const float* wt, const float* scale3, const __nv_bfloat16* h3, __nv_bfloat16* d3,
+                          long long plane, int n, cudaStream_t st) {
+  const long long total = (long long)n * 1024 * 32;
+  brush_seed_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xhat, boxes, target, target_is_frame, wt,
+                                                                         scale3, h3, d3, plane, n);
+  return CHECK_LAUNCH();
+}
+
+int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
+                        __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st) {
+  brush_update_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(gpad, boxes, weight, g_out, z, zp, zplane, n);
+  return CHECK_LAUNCH();
+}
+
+}  // namespace ian

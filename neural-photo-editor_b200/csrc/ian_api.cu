@@ -1,0 +1,900 @@
+// ian_api.cu -- C-ABI of libian_b200.so (include/ian_b200.h): handle, weight preparation, per-batch
+// plans (activation buffers in HBM + tap-GEMM descriptors + TMA maps) and the layer schedules of the
+// IAN_simple graph (reference IAN_simple.py:56-241) for encode, decode, brush gradient and edit loop.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ian_b200.h"
+#include "edge.h"
+#include "tapgemm.h"
+
+using namespace ian;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// host-side bf16 helpers (round-to-nearest-even), independent of device headers
+// ------------------------------------------------------------------------------------------------
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct HostParam {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+};
+
+struct ParamSpec {
+  const char* name;
+  int ndim;
+  int64_t shape[4];
+};
+
+// reference checkpoint names / shapes (IAN_simple.py layer names)
+const ParamSpec kSimpleWeights[] = {
+    {"enc_conv1.W", 4, {128, 3, 5, 5}},    {"enc_conv1.b", 1, {128}},
+    {"enc_conv2.W", 4, {256, 128, 5, 5}},  {"enc_conv3.W", 4, {512, 256, 5, 5}},
+    {"enc_conv4.W", 4, {1024, 512, 5, 5}}, {"enc_fc1.W", 2, {16384, 1000}},
+    {"enc_mu.W", 2, {1000, 100}},          {"enc_logsigma.W", 2, {1000, 100}},
+    {"l_dec_fc2.W", 2, {100, 16384}},      {"dec_conv1.W", 4, {1024, 512, 5, 5}},
+    {"dec_conv2.W", 4, {512, 256, 5, 5}},  {"dec_conv3.W", 4, {256, 128, 5, 5}},
+    {"dec_out.W", 4, {128, 3, 5, 5}},
+};
+struct BnSpec { const char* name; int64_t c; };
+const BnSpec kSimpleBn[] = {{"bnorm2", 256},       {"bnorm3", 512},     {"bnorm4", 1024},  {"bnorm_enc_fc1", 1000},
+                            {"mu_bnorm", 100},     {"ls_bnorm", 100},   {"bnorm_dec_fc2", 16384},
+                            {"bnorm_dc1", 512},    {"bnorm_dc2", 256},  {"bnorm_dc3", 128}};
+const char* kBnFields[] = {"beta", "gamma", "mean", "inv_std"};
+
+enum LayerId {
+  L_ENC_CONV2 = 0, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3,
+  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_COUNT
+};
+const char* kLayerNames[L_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "l_dec_fc2", "dec_conv1",
+                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2"};
+
+struct DevWeights {           // one GEMM layer's B operand + epilogue vectors
+  __nv_bfloat16* b = nullptr;
+  long long plane = 0;
+  int ntiles = 0, Cout = 0, Cin = 0;
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+
+struct Plan;
+
+}  // namespace
+
+struct ian_handle {
+  int device = 0;
+  int model_kind = 0;
+  int path = IAN_PATH_TC;
+  bool finalized = false;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::map<std::string, HostParam> params;
+  DevWeights w[L_COUNT];
+  float* conv1_wt = nullptr;   // [75][128]
+  float* conv1_b = nullptr;    // [128]
+  float* decout_wt = nullptr;  // [25][128][4]
+  std::map<int, Plan*> plans;
+  int max_chunk = 512;
+  bool timing = false;
+  struct Timed { cudaEvent_t e0, e1; };
+  std::vector<Timed> timed[L_COUNT];
+  double time_ms[L_COUNT] = {0};
+  long long time_cnt[L_COUNT] = {0};
+};
+
+namespace {
+
+int fail(ian_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                            \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) return fail(h, IAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_TRY(h, expr)                                                                          \
+  do {                                                                                               \
+    int _n = (expr);                                                                                 \
+    if (_n < 0) return fail(h, IAN_ERR_CUDA, "%s: launch failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
+    (h)->launches += _n;                                                                             \
+  } while (0)
+
+struct Planes {               // NHWC split-plane activation tensor
+  __nv_bfloat16* p = nullptr;
+  long long plane = 0;
+};
+
+struct Plan {
+  int n = 0;
+  Planes a1, a2, a3, a4, f1, zp, h0, h1, h2, h3, d3, d2, d1, d0;
+  float *x = nullptr, *head = nullptr, *z = nullptr, *xhat = nullptr, *gpad = nullptr, *ws_fc1 = nullptr, *eps = nullptr;
+  float* target = nullptr;
+  int32_t* boxes = nullptr;
+  TapGemm g[L_COUNT];
+  TcMaps* maps[L_COUNT] = {nullptr};
+  std::vector<void*> allocs;
+};
+
+int alloc_planes(ian_handle* h, Plan* pl, Planes& t, long long elems) {
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, (size_t)elems * 2 * sizeof(__nv_bfloat16)));
+  CUDA_TRY(h, cudaMemsetAsync(p, 0, (size_t)elems * 2 * sizeof(__nv_bfloat16), h->stream));
+  pl->allocs.push_back(p);
+  t.p = (__nv_bfloat16*)p;
+  t.plane = elems;
+  return IAN_OK;
+}
+template <typename T>
+int alloc_buf(ian_handle* h, Plan* pl, T*& out, long long elems) {
+  void* p = nullptr;
+  CUDA_TRY(h, cudaMalloc(&p, (size_t)elems * sizeof(T)));
+  CUDA_TRY(h, cudaMemsetAsync(p, 0, (size_t)elems * sizeof(T), h->stream));
+  pl->allocs.push_back(p);
+  out = (T*)p;
+  return IAN_OK;
+}
+
+// ---- tap tables --------------------------------------------------------------------------------
+void taps_conv_s2(TapGemm& g) {           // enc_conv: y[p] = sum_i x[2p+i-2] W[i]   (IAN_simple.py:73-116)
+  g.nphase = 1;
+  g.phase[0] = {0, 25, 0, 0};
+  int t = 0;
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {
+      const int a = (i - 2) >> 1, r = (i - 2) & 1, b = (j - 2) >> 1, s = (j - 2) & 1;
+      g.taps[t++] = {(int16_t)(r * 2 + s), (int16_t)a, (int16_t)b, (int16_t)(i * 5 + j)};
+    }
+  g.sh = g.sw = 2;
+  g.osh = g.osw = 1;
+}
+void taps_deconv_s2(TapGemm& g) {         // dec_conv: y[2p+r] = sum_d x[p+d] W[2+2d-r]   (layers.py:436-483)
+  g.nphase = 4;
+  int t = 0;
+  for (int r = 0; r < 2; ++r)
+    for (int s = 0; s < 2; ++s) {
+      Phase& ph = g.phase[r * 2 + s];
+      ph.tap_begin = t;
+      ph.oh0 = r;
+      ph.ow0 = s;
+      for (int d = (r ? 0 : -1); d <= 1; ++d)
+        for (int e = (s ? 0 : -1); e <= 1; ++e) {
+          const int ki = 2 + 2 * d - r, kj = 2 + 2 * e - s;
+          g.taps[t++] = {0, (int16_t)d, (int16_t)e, (int16_t)(ki * 5 + kj)};
+        }
+      ph.ntaps = t - ph.tap_begin;
+    }
+  g.sh = g.sw = 1;
+  g.osh = g.osw = 2;
+}
+void taps_deconv_bwd(TapGemm& g) {        // dx[a] = sum_ki dy[2+2a-ki] W[ki]   (T.grad of the above, API.py:59,64)
+  g.nphase = 1;
+  g.phase[0] = {0, 25, 0, 0};
+  int t = 0;
+  for (int ki = 0; ki < 5; ++ki)
+    for (int kj = 0; kj < 5; ++kj) {
+      const int e = 2 - ki, f = 2 - kj;
+      g.taps[t++] = {(int16_t)((e & 1) * 2 + (f & 1)), (int16_t)(e >> 1), (int16_t)(f >> 1), (int16_t)(ki * 5 + kj)};
+    }
+  g.sh = g.sw = 2;
+  g.osh = g.osw = 1;
+}
+void taps_dense(TapGemm& g) {
+  g.nphase = 1;
+  g.phase[0] = {0, 1, 0, 0};
+  g.taps[0] = {0, 0, 0, 0};
+  g.sh = g.sw = 1;
+  g.osh = g.osw = 1;
+}
+
+void set_io(TapGemm& g, const Planes& a, int n, int Hin, int Win, int Cin, int Hg, int Wg, const DevWeights& w,
+            int Hout, int Wout) {
+  g.a = a.p; g.a_plane = a.plane;
+  g.n_img = n; g.Hin = Hin; g.Win = Win; g.Cin = Cin; g.Hg = Hg; g.Wg = Wg;
+  g.b = w.b; g.b_plane = w.plane; g.Cout = w.Cout;
+  g.scale = w.scale; g.shift = w.shift; g.scale_pix_stride = 0;
+  g.Hout = Hout; g.Wout = Wout;
+  g.ksplit = 1; g.ws = nullptr; g.mask = nullptr; g.out = nullptr; g.out_f32 = nullptr; g.out_plane = 0;
+}
+
+int choose_ksplit(const TapGemm& g) {
+  // fill ~one wave of 148 SMs when the output tile count is small; keep >= 4 K steps per CTA
+  const int bn = (g.Cout % 256 == 0) ? 256 : 128;
+  const int M = g.n_img * g.Hg * g.Wg;
+  const int ctas = ((M + 127) / 128) * (g.Cout / bn) * g.nphase;
+  int min_it = 1 << 30;
+  for (int p = 0; p < g.nphase; ++p) {
+    const int it = g.phase[p].ntaps * (g.Cin / 64);
+    if (it < min_it) min_it = it;
+  }
+  int ks = 148 / ctas;
+  if (ks > min_it / 4) ks = min_it / 4;
+  if (ks < 1) ks = 1;
+  if (ks > 64) ks = 64;
+  return ks;
+}
+
+int build_plan(ian_handle* h, int n, Plan** out) {
+  Plan* pl = new Plan();
+  pl->n = n;
+  const long long N = n;
+  int rc;
+#define AP(t, e) if ((rc = alloc_planes(h, pl, pl->t, (e))) != IAN_OK) return rc;
+  AP(a1, N * 32 * 32 * 128) AP(a2, N * 16 * 16 * 256) AP(a3, N * 8 * 8 * 512) AP(a4, N * 4 * 4 * 1024)
+  AP(f1, N * 1024) AP(zp, N * 128)
+  AP(h0, N * 16384) AP(h1, N * 8 * 8 * 512) AP(h2, N * 16 * 16 * 256) AP(h3, N * 32 * 32 * 128)
+  AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
+#undef AP
+#define AB(t, e) if ((rc = alloc_buf(h, pl, pl->t, (e))) != IAN_OK) return rc;
+  AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(gpad, N * 128)
+  AB(ws_fc1, N * 1024) AB(eps, N * 100) AB(target, N * 3 * 4096) AB(boxes, N * 4)
+#undef AB
+
+  TapGemm* g = pl->g;
+  memset(g, 0, sizeof(TapGemm) * L_COUNT);
+  // ---- encoder (IAN_simple.py:84-126)
+  set_io(g[L_ENC_CONV2], pl->a1, n, 32, 32, 128, 16, 16, h->w[L_ENC_CONV2], 16, 16); taps_conv_s2(g[L_ENC_CONV2]);
+  g[L_ENC_CONV2].act = ACT_LRELU; g[L_ENC_CONV2].out = pl->a2.p; g[L_ENC_CONV2].out_plane = pl->a2.plane;
+  set_io(g[L_ENC_CONV3], pl->a2, n, 16, 16, 256, 8, 8, h->w[L_ENC_CONV3], 8, 8); taps_conv_s2(g[L_ENC_CONV3]);
+  g[L_ENC_CONV3].act = ACT_LRELU; g[L_ENC_CONV3].out = pl->a3.p; g[L_ENC_CONV3].out_plane = pl->a3.plane;
+  set_io(g[L_ENC_CONV4], pl->a3, n, 8, 8, 512, 4, 4, h->w[L_ENC_CONV4], 4, 4); taps_conv_s2(g[L_ENC_CONV4]);
+  g[L_ENC_CONV4].act = ACT_LRELU; g[L_ENC_CONV4].out = pl->a4.p; g[L_ENC_CONV4].out_plane = pl->a4.plane;
+  set_io(g[L_ENC_FC1], pl->a4, n, 1, 1, 16384, 1, 1, h->w[L_ENC_FC1], 1, 1); taps_dense(g[L_ENC_FC1]);
+  g[L_ENC_FC1].act = ACT_ELU; g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ws = pl->ws_fc1;
+  set_io(g[L_ENC_HEAD], pl->f1, n, 1, 1, 1024, 1, 1, h->w[L_ENC_HEAD], 1, 1); taps_dense(g[L_ENC_HEAD]);
+  g[L_ENC_HEAD].act = ACT_NONE; g[L_ENC_HEAD].out_f32 = pl->head;
+  // ---- decoder (IAN_simple.py:129-170)
+  set_io(g[L_DEC_FC2], pl->zp, n, 1, 1, 128, 1, 1, h->w[L_DEC_FC2], 1, 1); taps_dense(g[L_DEC_FC2]);
+  g[L_DEC_FC2].act = ACT_RELU; g[L_DEC_FC2].out = pl->h0.p; g[L_DEC_FC2].out_plane = pl->h0.plane;
+  set_io(g[L_DEC_CONV1], pl->h0, n, 4, 4, 1024, 4, 4, h->w[L_DEC_CONV1], 8, 8); taps_deconv_s2(g[L_DEC_CONV1]);
+  g[L_DEC_CONV1].act = ACT_RELU; g[L_DEC_CONV1].out = pl->h1.p; g[L_DEC_CONV1].out_plane = pl->h1.plane;
+  set_io(g[L_DEC_CONV2], pl->h1, n, 8, 8, 512, 8, 8, h->w[L_DEC_CONV2], 16, 16); taps_deconv_s2(g[L_DEC_CONV2]);
+  g[L_DEC_CONV2].act = ACT_RELU; g[L_DEC_CONV2].out = pl->h2.p; g[L_DEC_CONV2].out_plane = pl->h2.plane;
+  set_io(g[L_DEC_CONV3], pl->h2, n, 16, 16, 256, 16, 16, h->w[L_DEC_CONV3], 32, 32); taps_deconv_s2(g[L_DEC_CONV3]);
+  g[L_DEC_CONV3].act = ACT_RELU; g[L_DEC_CONV3].out = pl->h3.p; g[L_DEC_CONV3].out_plane = pl->h3.plane;
+  // ---- decoder backward-data for the latent brush (T.grad at API.py:59,64)
+  set_io(g[L_BWD_CONV3], pl->d3, n, 32, 32, 128, 16, 16, h->w[L_BWD_CONV3], 16, 16); taps_deconv_bwd(g[L_BWD_CONV3]);
+  g[L_BWD_CONV3].act = ACT_MASK; g[L_BWD_CONV3].mask = pl->h2.p; g[L_BWD_CONV3].out = pl->d2.p; g[L_BWD_CONV3].out_plane = pl->d2.plane;
+  set_io(g[L_BWD_CONV2], pl->d2, n, 16, 16, 256, 8, 8, h->w[L_BWD_CONV2], 8, 8); taps_deconv_bwd(g[L_BWD_CONV2]);
+  g[L_BWD_CONV2].act = ACT_MASK; g[L_BWD_CONV2].mask = pl->h1.p; g[L_BWD_CONV2].out = pl->d1.p; g[L_BWD_CONV2].out_plane = pl->d1.plane;
+  set_io(g[L_BWD_CONV1], pl->d1, n, 8, 8, 512, 4, 4, h->w[L_BWD_CONV1], 4, 4); taps_deconv_bwd(g[L_BWD_CONV1]);
+  g[L_BWD_CONV1].act = ACT_MASK; g[L_BWD_CONV1].mask = pl->h0.p; g[L_BWD_CONV1].out = pl->d0.p; g[L_BWD_CONV1].out_plane = pl->d0.plane;
+  g[L_BWD_CONV1].scale_pix_stride = 1024;   // bnorm_dec_fc2 is per FEATURE (pixel, channel)
+  set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
+  g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
+
+  for (int l = 0; l < L_COUNT; ++l) {
+    char err[256] = {0};
+    pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
+    if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
+    if (g[l].ws) {
+      g[l].ksplit = choose_ksplit(g[l]);
+      if (g[l].ksplit == 1) g[l].ws = nullptr;
+    }
+  }
+  // the split-K finalize of dz writes its result in place (ws == out_f32): finalize reads then writes
+  *out = pl;
+  return IAN_OK;
+}
+
+void free_plan(Plan* pl) {
+  for (void* p : pl->allocs) cudaFree(p);
+  for (int l = 0; l < L_COUNT; ++l) tc_free_maps(pl->maps[l]);
+  delete pl;
+}
+
+int get_plan(ian_handle* h, int n, Plan** out) {
+  auto it = h->plans.find(n);
+  if (it != h->plans.end()) { *out = it->second; return IAN_OK; }
+  Plan* pl = nullptr;
+  int rc = build_plan(h, n, &pl);
+  if (rc != IAN_OK) { if (pl) free_plan(pl); return rc; }
+  h->plans[n] = pl;
+  *out = pl;
+  return IAN_OK;
+}
+
+// ---- one tap-GEMM layer -------------------------------------------------------------------------
+int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
+  TapGemm g = pl->g[l];
+  ian_handle::Timed tm{};
+  if (h->timing) {
+    CUDA_TRY(h, cudaEventCreate(&tm.e0));
+    CUDA_TRY(h, cudaEventCreate(&tm.e1));
+  }
+  if (h->path == IAN_PATH_SIMT) {
+    g.ksplit = 1;
+    g.ws = nullptr;
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
+    LAUNCH_TRY(h, launch_tapgemm_simt(g, st));
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
+  } else {
+    if (g.ksplit > 1)
+      CUDA_TRY(h, cudaMemsetAsync(g.ws, 0, (size_t)g.n_img * g.Hout * g.Wout * g.Cout * sizeof(float), st));
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
+    LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
+    if (g.ksplit > 1) LAUNCH_TRY(h, launch_splitk_finalize(g, st));
+  }
+  if (h->timing) h->timed[l].push_back(tm);
+  return IAN_OK;
+}
+
+int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float* z, cudaStream_t st) {
+  const int n = pl->n;
+  LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+  int rc;
+  for (int l : {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD})
+    if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_sample(pl->head, eps, z, pl->zp.p, pl->zp.plane, n, st));
+  return IAN_OK;
+}
+
+// zp must already hold the latent planes
+int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
+  int rc;
+  for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
+    if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
+  return IAN_OK;
+}
+
+int run_decode(ian_handle* h, Plan* pl, const float* z, float* xhat, cudaStream_t st) {
+  LAUNCH_TRY(h, launch_z_to_planes(z, pl->zp.p, pl->zp.plane, pl->n, st));
+  return run_decode_from_planes(h, pl, xhat, st);
+}
+
+// decoder forward (from zp) + backward; leaves g (n,128 padded) in pl->gpad
+int run_grad_core(ian_handle* h, Plan* pl, const int32_t* boxes, const float* target, int target_is_frame,
+                  cudaStream_t st) {
+  int rc;
+  if ((rc = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_brush_seed_bwd(pl->xhat, boxes, target, target_is_frame, h->decout_wt, h->w[L_DEC_CONV3].scale,
+                                      pl->h3.p, pl->d3.p, pl->d3.plane, pl->n, st));
+  for (int l : {L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2})
+    if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  return IAN_OK;
+}
+
+int check_ready(ian_handle* h, int n, const void* a, const void* b) {
+  if (!h) return IAN_ERR_INVALID;
+  if (!h->finalized) return fail(h, IAN_ERR_STATE, "ian_finalize() has not been called");
+  if (n <= 0) return fail(h, IAN_ERR_INVALID, "batch size must be positive (got %d)", n);
+  if (!a || !b) return fail(h, IAN_ERR_INVALID, "NULL tensor pointer");
+  return IAN_OK;
+}
+
+int validate_boxes(ian_handle* h, const int32_t* bx, int n) {
+  for (int k = 0; k < n; ++k) {
+    const int c1 = bx[4 * k], r1 = bx[4 * k + 1], c2 = bx[4 * k + 2], r2 = bx[4 * k + 3];
+    if (c1 < 0 || r1 < 0 || c2 > 64 || r2 > 64 || c1 >= c2 || r1 >= r2)
+      return fail(h, IAN_ERR_INVALID, "box %d = [c1=%d,r1=%d,c2=%d,r2=%d] is empty or outside the 64x64 frame", k, c1, r1, c2, r2);
+  }
+  return IAN_OK;
+}
+
+// ---- weight preparation --------------------------------------------------------------------------
+const HostParam& P(ian_handle* h, const char* name) { return h->params[name]; }
+
+int upload_gemm_weights(ian_handle* h, int l, const std::vector<float>& B, int ntiles, int Cout, int Cin,
+                        const std::vector<float>& scale, const std::vector<float>& shift) {
+  DevWeights& w = h->w[l];
+  const long long elems = (long long)ntiles * Cout * Cin;
+  std::vector<uint16_t> planes((size_t)elems * 2);
+  for (long long i = 0; i < elems; ++i) {
+    const uint16_t hi = f2bf(B[i]);
+    planes[i] = hi;
+    planes[elems + i] = f2bf(B[i] - bf2f(hi));
+  }
+  CUDA_TRY(h, cudaMalloc((void**)&w.b, planes.size() * 2));
+  CUDA_TRY(h, cudaMemcpy(w.b, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+  w.plane = elems; w.ntiles = ntiles; w.Cout = Cout; w.Cin = Cin;
+  CUDA_TRY(h, cudaMalloc((void**)&w.scale, scale.size() * 4));
+  CUDA_TRY(h, cudaMemcpy(w.scale, scale.data(), scale.size() * 4, cudaMemcpyHostToDevice));
+  if (!shift.empty()) {
+    CUDA_TRY(h, cudaMalloc((void**)&w.shift, shift.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(w.shift, shift.data(), shift.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return IAN_OK;
+}
+
+// inference BatchNorm folded to y = x*scale + shift (lasagne batch_norm, IAN_simple.py:84-170)
+void fold_bn(ian_handle* h, const std::string& name, int c, std::vector<float>& scale, std::vector<float>& shift) {
+  const auto& be = P(h, (name + ".beta").c_str()).data;
+  const auto& ga = P(h, (name + ".gamma").c_str()).data;
+  const auto& me = P(h, (name + ".mean").c_str()).data;
+  const auto& is = P(h, (name + ".inv_std").c_str()).data;
+  scale.resize(c);
+  shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    scale[i] = ga[i] * is[i];
+    shift[i] = be[i] - me[i] * scale[i];
+  }
+}
+
+int prepare_simple(ian_handle* h) {
+  int rc;
+  std::vector<float> B, sc, sf;
+  // enc_conv2..4: B[i*5+j][o][c] = W[o][c][i][j]
+  struct CS { int l; const char* w; const char* bn; int Cout, Cin; } convs[] = {
+      {L_ENC_CONV2, "enc_conv2.W", "bnorm2", 256, 128}, {L_ENC_CONV3, "enc_conv3.W", "bnorm3", 512, 256},
+      {L_ENC_CONV4, "enc_conv4.W", "bnorm4", 1024, 512}};
+  for (auto& c : convs) {
+    const auto& W = P(h, c.w).data;
+    B.assign((size_t)25 * c.Cout * c.Cin, 0.f);
+    for (int o = 0; o < c.Cout; ++o)
+      for (int ci = 0; ci < c.Cin; ++ci)
+        for (int t = 0; t < 25; ++t) B[((size_t)t * c.Cout + o) * c.Cin + ci] = W[((size_t)o * c.Cin + ci) * 25 + t];
+    fold_bn(h, c.bn, c.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, c.l, B, 25, c.Cout, c.Cin, sc, sf)) != IAN_OK) return rc;
+  }
+  // enc_fc1: rows of W are flatten(NCHW) = c*16 + hw; our A is NHWC = hw*1024 + c.  Cout 1000 -> 1024.
+  {
+    const auto& W = P(h, "enc_fc1.W").data;
+    B.assign((size_t)1024 * 16384, 0.f);
+    for (int c = 0; c < 1024; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const float* src = &W[((size_t)c * 16 + hw) * 1000];
+        for (int o = 0; o < 1000; ++o) B[(size_t)o * 16384 + hw * 1024 + c] = src[o];
+      }
+    fold_bn(h, "bnorm_enc_fc1", 1000, sc, sf);
+    sc.resize(1024, 0.f);
+    sf.resize(1024, 0.f);
+    if ((rc = upload_gemm_weights(h, L_ENC_FC1, B, 1, 1024, 16384, sc, sf)) != IAN_OK) return rc;
+  }
+  // head: mu (cols 0..99) | logsigma (cols 100..199), Cout 200 -> 256, Cin 1000 -> 1024
+  {
+    const auto& Wm = P(h, "enc_mu.W").data;
+    const auto& Wl = P(h, "enc_logsigma.W").data;
+    B.assign((size_t)256 * 1024, 0.f);
+    for (int k = 0; k < 1000; ++k)
+      for (int o = 0; o < 100; ++o) {
+        B[(size_t)o * 1024 + k] = Wm[(size_t)k * 100 + o];
+        B[(size_t)(100 + o) * 1024 + k] = Wl[(size_t)k * 100 + o];
+      }
+    std::vector<float> s1, f1, s2, f2;
+    fold_bn(h, "mu_bnorm", 100, s1, f1);
+    fold_bn(h, "ls_bnorm", 100, s2, f2);
+    sc.assign(256, 0.f);
+    sf.assign(256, 0.f);
+    for (int o = 0; o < 100; ++o) { sc[o] = s1[o]; sf[o] = f1[o]; sc[100 + o] = s2[o]; sf[100 + o] = f2[o]; }
+    if ((rc = upload_gemm_weights(h, L_ENC_HEAD, B, 1, 256, 1024, sc, sf)) != IAN_OK) return rc;
+  }
+  // l_dec_fc2: reference column j = c*16 + hw -> our column hw*1024 + c; Cin 100 -> 128
+  std::vector<float> sc0, sf0;
+  {
+    const auto& W = P(h, "l_dec_fc2.W").data;
+    B.assign((size_t)16384 * 128, 0.f);
+    std::vector<float> s, f;
+    fold_bn(h, "bnorm_dec_fc2", 16384, s, f);
+    sc0.resize(16384);
+    sf0.resize(16384);
+    for (int c = 0; c < 1024; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 1024 + c;
+        sc0[col] = s[j];
+        sf0[col] = f[j];
+        for (int k = 0; k < 100; ++k) B[(size_t)col * 128 + k] = W[(size_t)k * 16384 + j];
+      }
+    if ((rc = upload_gemm_weights(h, L_DEC_FC2, B, 1, 16384, 128, sc0, sf0)) != IAN_OK) return rc;
+    // backward: dz[k] = sum_col d0[col] * W[k][col]  -> B[k][col], Cout 100 -> 128
+    B.assign((size_t)128 * 16384, 0.f);
+    for (int c = 0; c < 1024; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 1024 + c;
+        for (int k = 0; k < 100; ++k) B[(size_t)k * 16384 + col] = W[(size_t)k * 16384 + j];
+      }
+    std::vector<float> ones(128, 1.f);
+    if ((rc = upload_gemm_weights(h, L_BWD_FC2, B, 1, 128, 16384, ones, {})) != IAN_OK) return rc;
+  }
+  // dec_conv1..3: W (Cin,Cout,5,5).  forward B[k][co][ci] = W[ci][co][k]; backward B[k][ci][co] = W[ci][co][k]
+  struct DS { int lf, lb; const char* w; const char* bn; int Cin, Cout; } decs[] = {
+      {L_DEC_CONV1, L_BWD_CONV1, "dec_conv1.W", "bnorm_dc1", 1024, 512},
+      {L_DEC_CONV2, L_BWD_CONV2, "dec_conv2.W", "bnorm_dc2", 512, 256},
+      {L_DEC_CONV3, L_BWD_CONV3, "dec_conv3.W", "bnorm_dc3", 256, 128}};
+  std::vector<float> prev_scale = sc0;   // scale applied in the backward epilogue = BN scale of the layer BELOW
+  std::vector<std::vector<float>> fwd_scales;
+  for (auto& d : decs) {
+    const auto& W = P(h, d.w).data;
+    B.assign((size_t)25 * d.Cout * d.Cin, 0.f);
+    for (int ci = 0; ci < d.Cin; ++ci)
+      for (int co = 0; co < d.Cout; ++co)
+        for (int t = 0; t < 25; ++t) B[((size_t)t * d.Cout + co) * d.Cin + ci] = W[((size_t)ci * d.Cout + co) * 25 + t];
+    fold_bn(h, d.bn, d.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, d.lf, B, 25, d.Cout, d.Cin, sc, sf)) != IAN_OK) return rc;
+    for (int ci = 0; ci < d.Cin; ++ci)
+      for (int co = 0; co < d.Cout; ++co)
+        for (int t = 0; t < 25; ++t) B[((size_t)t * d.Cin + ci) * d.Cout + co] = W[((size_t)ci * d.Cout + co) * 25 + t];
+    // backward GEMM of this layer produces the gradient w.r.t. its INPUT activation, whose BN scale is prev_scale
+    if ((rc = upload_gemm_weights(h, d.lb, B, 25, d.Cin, d.Cout, prev_scale, {})) != IAN_OK) return rc;
+    prev_scale = sc;
+  }
+  // conv1: wt[(c*5+i)*5+j][o] = W[o][c][i][j]
+  {
+    const auto& W = P(h, "enc_conv1.W").data;
+    std::vector<float> wt(75 * 128);
+    for (int o = 0; o < 128; ++o)
+      for (int k = 0; k < 75; ++k) wt[k * 128 + o] = W[o * 75 + k];
+    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_wt, wt.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->conv1_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    const auto& b = P(h, "enc_conv1.b").data;
+    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_b, 128 * 4));
+    CUDA_TRY(h, cudaMemcpy(h->conv1_b, b.data(), 128 * 4, cudaMemcpyHostToDevice));
+  }
+  // dec_out: wt[ki*5+kj][ci][co(4)] = W[ci][co][ki][kj]
+  {
+    const auto& W = P(h, "dec_out.W").data;
+    std::vector<float> wt(25 * 128 * 4, 0.f);
+    for (int ci = 0; ci < 128; ++ci)
+      for (int co = 0; co < 3; ++co)
+        for (int t = 0; t < 25; ++t) wt[(t * 128 + ci) * 4 + co] = W[(ci * 3 + co) * 25 + t];
+    CUDA_TRY(h, cudaMalloc((void**)&h->decout_wt, wt.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->decout_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return IAN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename F>
+int for_chunks(ian_handle* h, int n, F&& f) {
+  for (int off = 0; off < n; off += h->max_chunk) {
+    const int cn = (n - off < h->max_chunk) ? n - off : h->max_chunk;
+    Plan* pl = nullptr;
+    int rc = get_plan(h, cn, &pl);
+    if (rc != IAN_OK) return rc;
+    if ((rc = f(pl, off, cn)) != IAN_OK) return rc;
+  }
+  return IAN_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int ian_create(int model_kind, int device, ian_handle** out) {
+  if (!out) return fail(nullptr, IAN_ERR_INVALID, "out is NULL");
+  if (model_kind != IAN_MODEL_SIMPLE) return fail(nullptr, IAN_ERR_UNSUPPORTED, "unknown model kind %d", model_kind);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, IAN_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, IAN_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return fail(nullptr, IAN_ERR_UNSUPPORTED, "device %d is sm_%d%d; libian_b200 is built for sm_100a only", device, prop.major, prop.minor);
+  ian_handle* h = new ian_handle();
+  h->device = device;
+  h->model_kind = model_kind;
+  DeviceGuard dg(device);
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, IAN_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
+  if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
+  *out = h;
+  return IAN_OK;
+}
+
+int ian_set_param(ian_handle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || !shape) return fail(h, IAN_ERR_INVALID, "NULL argument");
+  if (h->finalized) return fail(h, IAN_ERR_STATE, "model already finalized");
+  const ParamSpec* spec = nullptr;
+  ParamSpec bn_spec;
+  for (const auto& s : kSimpleWeights)
+    if (!strcmp(s.name, name)) spec = &s;
+  if (!spec) {
+    for (const auto& b : kSimpleBn)
+      for (const char* f : kBnFields) {
+        std::string full = std::string(b.name) + "." + f;
+        if (full == name) { bn_spec = {name, 1, {b.c}}; spec = &bn_spec; }
+      }
+  }
+  if (!spec) return fail(h, IAN_ERR_INVALID, "unknown parameter name '%s'", name);
+  if (ndim != spec->ndim) return fail(h, IAN_ERR_INVALID, "parameter %s: expected %d dims, got %d", name, spec->ndim, ndim);
+  int64_t elems = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] != spec->shape[i])
+      return fail(h, IAN_ERR_INVALID, "parameter %s: shape mismatch at dim %d (expected %lld, got %lld)", name, i,
+                  (long long)spec->shape[i], (long long)shape[i]);
+    elems *= shape[i];
+  }
+  HostParam& p = h->params[name];
+  p.shape.assign(shape, shape + ndim);
+  p.data.assign(data, data + elems);
+  return IAN_OK;
+}
+
+int ian_finalize(ian_handle* h) {
+  if (!h) return IAN_ERR_INVALID;
+  if (h->finalized) return IAN_OK;
+  for (const auto& s : kSimpleWeights)
+    if (!h->params.count(s.name)) return fail(h, IAN_ERR_STATE, "missing parameter '%s'", s.name);
+  for (const auto& b : kSimpleBn)
+    for (const char* f : kBnFields) {
+      std::string full = std::string(b.name) + "." + f;
+      if (!h->params.count(full)) return fail(h, IAN_ERR_STATE, "missing parameter '%s'", full.c_str());
+    }
+  DeviceGuard dg(h->device);
+  int rc = prepare_simple(h);
+  if (rc != IAN_OK) return rc;
+  h->params.clear();
+  h->finalized = true;
+  return IAN_OK;
+}
+
+int ian_destroy(ian_handle* h) {
+  if (!h) return IAN_OK;
+  DeviceGuard dg(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->plans) free_plan(kv.second);
+  for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
+  cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt);
+  for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return IAN_OK;
+}
+
+const char* ian_last_error(const ian_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int ian_get_zdim(const ian_handle*) { return 100; }
+int64_t ian_launch_count(const ian_handle* h) { return h ? h->launches : 0; }
+
+int ian_set_path(ian_handle* h, int path) {
+  if (!h) return IAN_ERR_INVALID;
+  if (path != IAN_PATH_TC && path != IAN_PATH_SIMT) return fail(h, IAN_ERR_INVALID, "unknown path %d", path);
+  h->path = path;
+  return IAN_OK;
+}
+
+int ian_set_layer_timing(ian_handle* h, int enable) {
+  if (!h) return IAN_ERR_INVALID;
+  h->timing = enable != 0;
+  return IAN_OK;
+}
+
+double ian_layer_time_ms(ian_handle* h, const char* layer_name, int reset) {
+  if (!h || !layer_name) return -1.0;
+  DeviceGuard dg(h->device);
+  for (int l = 0; l < L_COUNT; ++l) {
+    if (strcmp(kLayerNames[l], layer_name)) continue;
+    for (auto& t : h->timed[l]) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+        h->time_ms[l] += ms;
+        h->time_cnt[l] += 1;
+      }
+      cudaEventDestroy(t.e0);
+      cudaEventDestroy(t.e1);
+    }
+    h->timed[l].clear();
+    const double r = h->time_cnt[l] ? h->time_ms[l] / (double)h->time_cnt[l] : -1.0;
+    if (reset) { h->time_ms[l] = 0; h->time_cnt[l] = 0; }
+    return r;
+  }
+  return -1.0;
+}
+
+// ---- encode ---------------------------------------------------------------------------------------
+int ian_encode_dev(ian_handle* h, const float* x, int n, const float* eps, float* z, void* stream) {
+  int rc = check_ready(h, n, x, z);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return for_chunks(h, n, [&](Plan* pl, int off, int) {
+    return run_encode(h, pl, x + (size_t)off * 12288, eps ? eps + (size_t)off * 100 : nullptr, z + (size_t)off * 100, st);
+  });
+}
+
+int ian_encode_host(ian_handle* h, const float* x, int n, const float* eps, float* z) {
+  int rc = check_ready(h, n, x, z);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->x, x + (size_t)off * 12288, (size_t)cn * 12288 * 4, cudaMemcpyHostToDevice, st));
+    if (eps) CUDA_TRY(h, cudaMemcpyAsync(pl->eps, eps + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
+    int r = run_encode(h, pl, pl->x, eps ? pl->eps : nullptr, pl->z, st);
+    if (r != IAN_OK) return r;
+    CUDA_TRY(h, cudaMemcpyAsync(z + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// ---- decode ---------------------------------------------------------------------------------------
+int ian_decode_dev(ian_handle* h, const float* z, int n, float* x, void* stream) {
+  int rc = check_ready(h, n, z, x);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return for_chunks(h, n, [&](Plan* pl, int off, int) {
+    return run_decode(h, pl, z + (size_t)off * 100, x + (size_t)off * 12288, st);
+  });
+}
+
+int ian_decode_host(ian_handle* h, const float* z, int n, float* x) {
+  int rc = check_ready(h, n, z, x);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->z, z + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
+    int r = run_decode(h, pl, pl->z, pl->xhat, st);
+    if (r != IAN_OK) return r;
+    CUDA_TRY(h, cudaMemcpyAsync(x + (size_t)off * 12288, pl->xhat, (size_t)cn * 12288 * 4, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// ---- encode -> decode -----------------------------------------------------------------------------
+int ian_reconstruct_dev(ian_handle* h, const float* x, int n, float* z_out, float* x_hat, void* stream) {
+  int rc = check_ready(h, n, x, x_hat);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  return for_chunks(h, n, [&](Plan* pl, int off, int) {
+    int r = run_encode(h, pl, x + (size_t)off * 12288, nullptr, z_out ? z_out + (size_t)off * 100 : nullptr, st);
+    if (r != IAN_OK) return r;
+    return run_decode_from_planes(h, pl, x_hat + (size_t)off * 12288, st);
+  });
+}
+
+int ian_reconstruct_host(ian_handle* h, const float* x, int n, float* z_out, float* x_hat) {
+  int rc = check_ready(h, n, x, x_hat);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->x, x + (size_t)off * 12288, (size_t)cn * 12288 * 4, cudaMemcpyHostToDevice, st));
+    int r = run_encode(h, pl, pl->x, nullptr, pl->z, st);
+    if (r != IAN_OK) return r;
+    if ((r = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return r;
+    if (z_out) CUDA_TRY(h, cudaMemcpyAsync(z_out + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)off * 12288, pl->xhat, (size_t)cn * 12288 * 4, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// ---- brush gradient -------------------------------------------------------------------------------
+int ian_grad_dev(ian_handle* h, const float* z, const int32_t* boxes, const float* target, int target_is_frame, int n,
+                 float* g, void* stream) {
+  int rc = check_ready(h, n, z, g);
+  if (rc != IAN_OK) return rc;
+  if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t tstride = target_is_frame ? 12288 : 3;
+  return for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    LAUNCH_TRY(h, launch_z_to_planes(z + (size_t)off * 100, pl->zp.p, pl->zp.plane, cn, st));
+    int r = run_grad_core(h, pl, boxes + (size_t)off * 4, target ? target + off * tstride : nullptr, target_is_frame, st);
+    if (r != IAN_OK) return r;
+    LAUNCH_TRY(h, launch_brush_update(pl->gpad, boxes + (size_t)off * 4, 0.f, g + (size_t)off * 100, nullptr, nullptr, 0, cn, st));
+    return (int)IAN_OK;
+  });
+}
+
+int ian_grad_host(ian_handle* h, const float* z, const int32_t* boxes, const float* target, int target_is_frame, int n,
+                  float* g) {
+  int rc = check_ready(h, n, z, g);
+  if (rc != IAN_OK) return rc;
+  if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
+  if ((rc = validate_boxes(h, boxes, n)) != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  const size_t tstride = target_is_frame ? 12288 : 3;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->z, z + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(pl->boxes, boxes + (size_t)off * 4, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
+    if (target) CUDA_TRY(h, cudaMemcpyAsync(pl->target, target + off * tstride, cn * tstride * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
+    int r = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+    if (r != IAN_OK) return r;
+    LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, 0.f, pl->z /*reuse as g staging*/, nullptr, nullptr, 0, cn, st));
+    CUDA_TRY(h, cudaMemcpyAsync(g + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// ---- edit loop ------------------------------------------------------------------------------------
+int ian_edit_loop_dev(ian_handle* h, float* z, const int32_t* boxes, const float* target, int target_is_frame, int n,
+                      int n_steps, float weight, void* stream) {
+  int rc = check_ready(h, n, z, z);
+  if (rc != IAN_OK) return rc;
+  if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
+  if (n_steps < 0) return fail(h, IAN_ERR_INVALID, "n_steps < 0");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const size_t tstride = target_is_frame ? 12288 : 3;
+  return for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    float* zc = z + (size_t)off * 100;
+    LAUNCH_TRY(h, launch_z_to_planes(zc, pl->zp.p, pl->zp.plane, cn, st));
+    for (int s = 0; s < n_steps; ++s) {
+      int r = run_grad_core(h, pl, boxes + (size_t)off * 4, target ? target + off * tstride : nullptr, target_is_frame, st);
+      if (r != IAN_OK) return r;
+      LAUNCH_TRY(h, launch_brush_update(pl->gpad, boxes + (size_t)off * 4, weight, nullptr, zc, pl->zp.p, pl->zp.plane, cn, st));
+    }
+    return (int)IAN_OK;
+  });
+}
+
+int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const float* target, int target_is_frame, int n,
+                       int n_steps, float weight) {
+  int rc = check_ready(h, n, z, z);
+  if (rc != IAN_OK) return rc;
+  if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
+  if ((rc = validate_boxes(h, boxes, n)) != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  const size_t tstride = target_is_frame ? 12288 : 3;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->z, z + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(pl->boxes, boxes + (size_t)off * 4, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
+    if (target) CUDA_TRY(h, cudaMemcpyAsync(pl->target, target + off * tstride, cn * tstride * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
+    for (int s = 0; s < n_steps; ++s) {
+      int r = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+      if (r != IAN_OK) return r;
+      LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, cn, st));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(z + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+}  // extern "C"

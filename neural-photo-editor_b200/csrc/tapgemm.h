@@ -1,0 +1,95 @@
+// tapgemm.h -- the "shifted-tap GEMM": the one dense contraction every heavy IAN layer reduces to.
+//
+//   out[n, p*osh+oh0, q*osw+ow0, co] = epi( sum_t sum_c A[n, (p+dh_t)*sh + vh_t, (q+dw_t)*sw + vw_t, c]
+//                                                   * B[wtile_t][co][c] )
+//
+// with zero padding outside A.  It covers (reference file:line of the op each case replaces):
+//   * 5x5 stride-2 convolution, enc_conv2-4 (IAN_simple.py:84-116): 25 taps over the 4 stride-2
+//     "views" of the input (view = parity of the input row/col), one phase;
+//   * 5x5 stride-2 transposed convolution, dec_conv1-3 (layers.py:436-483): 4 output sub-pixel phases
+//     with 9/6/6/4 taps each over the plain input, output written at stride 2;
+//   * its backward-data for the latent brush (T.grad at API.py:59,64): a stride-2 5x5 conv again;
+//   * dense layers enc_fc1 / enc_mu|logsigma / l_dec_fc2 / dz (IAN_simple.py:117-135): 1 tap, 1x1 grid.
+//
+// Operands are bf16 SPLIT PLANES: a float32 value v is stored as hi=bf16(v), lo=bf16(v-hi) in two
+// planes of the same NHWC tensor (4 bytes/element, 16 significand bits).  The tensor-core path
+// computes hi*hi + lo*hi + hi*lo with fp32 accumulation (3 tcgen05 MMAs per K step); the SIMT path
+// computes (hi+lo)*(hi+lo) in fp32 FFMA.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ian {
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_ELU = 3, ACT_MASK = 4 };
+
+constexpr int kMaxTaps = 40;
+constexpr int kMaxPhases = 4;
+
+struct Tap {
+  int16_t view;   // 0..3 = (row parity << 1) | col parity of the strided input view
+  int16_t dh, dw; // shift in view coordinates
+  int16_t wtile;  // which [Cout][Cin] weight tile
+};
+
+struct Phase {
+  int tap_begin, ntaps;
+  int oh0, ow0;   // output offset of this phase
+};
+
+struct TapGemm {
+  // A: NHWC split planes
+  const __nv_bfloat16* a;
+  long long a_plane;            // elements between hi and lo plane
+  int n_img, Hin, Win, Cin;     // Cin % 64 == 0
+  int sh, sw;                   // view stride (1 or 2)
+  int Hg, Wg;                   // M grid: rows m = (n*Hg + p)*Wg + q
+  // B: [wtile][Cout][Cin] split planes, K(=Cin)-major
+  const __nv_bfloat16* b;
+  long long b_plane;
+  int Cout;                     // % 64 == 0 (padded by the host)
+  int nphase;
+  Phase phase[kMaxPhases];
+  Tap taps[kMaxTaps];
+  // epilogue: v = acc*scale[si] + shift[si]; v = act(v); ACT_MASK: v = acc*scale[si] * (mask>0)
+  const float* scale;
+  const float* shift;
+  int scale_pix_stride;         // si = co + (oh*Wout+ow)*scale_pix_stride
+  int act;
+  const __nv_bfloat16* mask;    // hi plane with the output's geometry (ACT_MASK)
+  // output: NHWC split planes and/or fp32, pixel = (n*Hout + p*osh+oh0)*Wout + q*osw+ow0
+  __nv_bfloat16* out;
+  long long out_plane;
+  float* out_f32;
+  int Hout, Wout, osh, osw;
+  // split-K (tensor-core path, small-M layers): raw accumulators are atomically added to ws, a
+  // finalize kernel applies the epilogue.
+  int ksplit;
+  float* ws;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case ACT_LRELU: return 0.6f * v + 0.4f * fabsf(v);       // lasagne LeakyRectify(0.2): f1*x+f2*|x|
+    case ACT_RELU:  return 0.5f * (v + fabsf(v));            // lasagne rectify
+    case ACT_ELU:   return v > 0.f ? v : expm1f(v);
+    default:        return v;
+  }
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---- launchers (each returns the number of kernels it launched, or <0 on error) -----------------
+int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st);
+// tensor-core path; maps are built by tc_build_maps() once per plan
+struct TcMaps;   // opaque: CUtensorMaps for A views and B
+TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen);
+void tc_free_maps(TcMaps*);
+int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st);
+int launch_splitk_finalize(const TapGemm& g, cudaStream_t st);
+
+}  // namespace ian

@@ -1,0 +1,160 @@
+// tapgemm_simt.cu -- fp32 FFMA implementation of the shifted-tap GEMM (see tapgemm.h).
+// This is the verification path (IAN_PATH_SIMT): it shares no arithmetic with the tcgen05 kernel
+// (operands are re-joined to fp32, products and sums are plain FFMA), so the two check each other on
+// the GPU.  Also hosts the split-K finalize kernel used by the tensor-core path.
+#include "tapgemm.h"
+
+namespace ian {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__device__ __forceinline__ float4 load_join4(const __nv_bfloat16* hi, long long plane) {
+  // 4 consecutive channels: hi and lo planes, 8 bytes each
+  uint2 h = *reinterpret_cast<const uint2*>(hi);
+  uint2 l = *reinterpret_cast<const uint2*>(hi + plane);
+  const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+  const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+  float2 h0 = __bfloat1622float2(hp[0]), h1 = __bfloat1622float2(hp[1]);
+  float2 l0 = __bfloat1622float2(lp[0]), l1 = __bfloat1622float2(lp[1]);
+  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+}
+
+__device__ __forceinline__ void epilogue_store(const TapGemm& g, float acc, long long pix, int oh, int ow,
+                                               int co, __nv_bfloat16* hi4, __nv_bfloat16* lo4,
+                                               float* f4, int j) {
+  int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
+  float sc = g.scale ? g.scale[si] : 1.f;
+  float v;
+  if (g.act == ACT_MASK) {
+    float mk = __bfloat162float(g.mask[pix * g.Cout + co]);
+    v = mk > 0.f ? acc * sc : 0.f;
+  } else {
+    float sf = g.shift ? g.shift[si] : 0.f;
+    v = act_apply(fmaf(acc, sc, sf), g.act);
+  }
+  f4[j] = v;
+  split_bf16(v, hi4[j], lo4[j]);
+}
+
+__global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant__ TapGemm g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const Phase ph = g.phase[blockIdx.z];
+  const int M = g.n_img * g.Hg * g.Wg;
+
+  // the row this thread loads for A
+  const int lr = tid >> 2, lc = (tid & 3) * 4;
+  const int lm = m0 + lr;
+  int ln = 0, lp = 0, lq = 0;
+  const bool lvalid = lm < M;
+  if (lvalid) {
+    lq = lm % g.Wg;
+    int t = lm / g.Wg;
+    lp = t % g.Hg;
+    ln = t / g.Hg;
+  }
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < ph.ntaps; ++t) {
+    const Tap tap = g.taps[ph.tap_begin + t];
+    const int vp = lp + tap.dh, vq = lq + tap.dw;
+    const int ih = vp * g.sh + (tap.view >> 1), iw = vq * g.sw + (tap.view & 1);
+    const bool ok = lvalid && vp >= 0 && vq >= 0 && ih < g.Hin && iw < g.Win;
+    const __nv_bfloat16* arow =
+        g.a + ((long long)(ln * g.Hin + ih) * g.Win + iw) * g.Cin + lc;
+    const __nv_bfloat16* brow =
+        g.b + ((long long)tap.wtile * g.Cout + (n0 + lr)) * g.Cin + lc;
+    for (int c0 = 0; c0 < g.Cin; c0 += BK) {
+      float4 av = ok ? load_join4(arow + c0, g.a_plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 bv = load_join4(brow + c0, g.b_plane);
+      __syncthreads();
+      As[lc + 0][lr] = av.x; As[lc + 1][lr] = av.y; As[lc + 2][lr] = av.z; As[lc + 3][lr] = av.w;
+      Bs[lc + 0][lr] = bv.x; Bs[lc + 1][lr] = bv.y; Bs[lc + 2][lr] = bv.z; Bs[lc + 3][lr] = bv.w;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+        float br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int q = m % g.Wg;
+    const int t2 = m / g.Wg;
+    const int p = t2 % g.Hg, n = t2 / g.Hg;
+    const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
+    const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
+    const int co = n0 + tx * 4;
+    __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+    __align__(16) float f4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) epilogue_store(g, acc[i][j], pix, oh, ow, co + j, hi4, lo4, f4, j);
+    if (g.out) {
+      *reinterpret_cast<uint2*>(g.out + pix * g.Cout + co) = *reinterpret_cast<uint2*>(hi4);
+      *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
+    }
+    if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co) = *reinterpret_cast<float4*>(f4);
+  }
+}
+
+// ws[pix][Cout] raw accumulators -> epilogue -> planes / f32.  One thread per 4 channels.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_constant__ TapGemm g, long long npix) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = g.Cout / 4;
+  if (idx >= npix * c4) return;
+  const long long pix = idx / c4;
+  const int co = (int)(idx % c4) * 4;
+  const int ow = (int)(pix % g.Wout);
+  const int oh = (int)((pix / g.Wout) % g.Hout);
+  float4 a = *reinterpret_cast<const float4*>(g.ws + pix * g.Cout + co);
+  float ar[4] = {a.x, a.y, a.z, a.w};
+  __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+  __align__(16) float f4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) epilogue_store(g, ar[j], pix, oh, ow, co + j, hi4, lo4, f4, j);
+  if (g.out) {
+    *reinterpret_cast<uint2*>(g.out + pix * g.Cout + co) = *reinterpret_cast<uint2*>(hi4);
+    *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
+  }
+  if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co) = *reinterpret_cast<float4*>(f4);
+}
+
+}  // namespace
+
+int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st) {
+  const int M = g.n_img * g.Hg * g.Wg;
+  dim3 grid((M + BM - 1) / BM, g.Cout / BN, g.nphase);
+  tapgemm_simt_kernel<<<grid, 256, 0, st>>>(g);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_splitk_finalize(const TapGemm& g, cudaStream_t st) {
+  const long long npix = (long long)g.n_img * g.Hout * g.Wout;
+  const long long total = npix * (g.Cout / 4);
+  splitk_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, npix);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ian

@@ -1,0 +1,398 @@
+// tapgemm_tc.cu -- tcgen05 / TMEM / TMA implementation of the shifted-tap GEMM (see tapgemm.h).
+//
+// One CTA computes a 128 (pixels) x BN (output channels) tile of one output phase:
+//   warp 0     : TMA producer.  Per K step (one tap x 64 input channels) two bulk-tensor loads:
+//                a 5-D box {64 ch, Wt, Ht, Nt, 2 planes} of the activation view the tap reads -- the
+//                tap shift is just a coordinate offset and the zero padding of the convolution is
+//                TMA's out-of-bounds fill -- and a 3-D box {64 ch, BN, 2 planes} of the tap's weights.
+//                Both land in the 128B-swizzled K-major layout tcgen05 consumes; no im2col buffer
+//                ever exists in HBM or shared memory.
+//   warp 1     : TMEM allocation + single-thread tcgen05.mma issue.  fp32 fidelity from bf16 tensor
+//                cores: per K=16 slice   main  += A_hi * B_hi
+//                                         cross += A_lo * B_hi ;  cross += A_hi * B_lo
+//                in two separate TMEM accumulators (the 2^-9-smaller cross terms get their own
+//                accumulator so their rounding does not ride on the main sum's exponent).
+//   warps 2..5 : epilogue.  tcgen05.ld both accumulators, add, BatchNorm scale/shift + activation
+//                (or backward scale * ReLU-mask), re-split to bf16 hi/lo planes and store NHWC at
+//                the phase's output stride; or atomically add raw sums for split-K.
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA -> tcgen05.commit).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "tapgemm.h"
+
+namespace ian {
+
+struct TcMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+  int Wt, Ht, Nt, BN;
+};
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kATileBytes = BM * BK * 2 * 2;            // hi + lo planes: 32 KB
+
+template <int BN> struct TcCfg {
+  static constexpr int kBTileBytes = BN * BK * 2 * 2;  // hi + lo
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kTmemCols = 2 * BN;             // main + cross accumulators
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a pipeline bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand descriptor (8-row x 128B atoms, SBO = 1024 B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: kind::f16, A/B = BF16 K-major, D = F32, M = 128, N = BN
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- kernel
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  // barriers: full[s] at +8s, empty[s] at +8(STAGES+s), tmem_full at +8*2*STAGES, tmem slot after
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * 2 * Cfg::kStages;
+  const uint32_t tmem_slot = tmem_full_bar + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
+  int mt = blockIdx.x;
+  const int qb = mt % tiles_q; mt /= tiles_q;
+  const int pb = mt % tiles_p; mt /= tiles_p;
+  const int n0 = mt * maps.Nt, p0 = pb * maps.Ht, q0 = qb * maps.Wt;
+  const int co0 = blockIdx.y * BN;
+  const int phase_idx = blockIdx.z / g.ksplit, ks = blockIdx.z % g.ksplit;
+  const Phase ph = g.phase[phase_idx];
+  const int nchunk = g.Cin / BK;
+  const int total_it = ph.ntaps * nchunk;
+  const int it0 = (int)((long long)total_it * ks / g.ksplit);
+  const int it1 = (int)((long long)total_it * (ks + 1) / g.ksplit);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int it = it0; it < it1; ++it) {
+        const int i = it - it0;
+        const int s = i % Cfg::kStages;
+        const uint32_t par = (uint32_t)((i / Cfg::kStages) & 1);
+        const Tap tap = g.taps[ph.tap_begin + it / nchunk];
+        const int c0 = (it % nchunk) * BK;
+        mbar_wait(empty_bar(s), par ^ 1u);
+        mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        tma_load_5d(&maps.a[tap.view], full_bar(s), sa, c0, q0 + tap.dw, p0 + tap.dh, n0, 0);
+        tma_load_3d(&maps.b, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + co0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      const uint32_t acc_main = tmem_base, acc_cross = tmem_base + BN;
+      for (int it = it0; it < it1; ++it) {
+        const int i = it - it0;
+        const int s = i % Cfg::kStages;
+        const uint32_t par = (uint32_t)((i / Cfg::kStages) & 1);
+        mbar_wait(full_bar(s), par);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + BM * BK * 2);
+        const uint64_t b_hi = make_sw128_desc(sa + kATileBytes), b_lo = make_sw128_desc(sa + kATileBytes + BN * BK * 2);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ko = (uint64_t)(k * 2);       // 32 bytes per K=16 slice, in 16-byte units
+          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+          umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+          umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+          umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+        }
+        umma_commit(empty_bar(s));                      // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                       // accumulators complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lg = warp & 3;                            // TMEM lane group this warp may access
+    const int ml = lg * 32 + lane;                      // tile row
+    const int wl = ml % maps.Wt;
+    const int hl = (ml / maps.Wt) % maps.Ht;
+    const int nl = ml / (maps.Wt * maps.Ht);
+    const int n = n0 + nl, p = p0 + hl, q = q0 + wl;
+    const bool valid = n < g.n_img;
+    const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
+    const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
+    if (it1 > it0) {
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t vm[32], vc[32];
+        tmem_ld32(lane_addr + cb, vm);
+        tmem_ld32(lane_addr + BN + cb, vc);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int co = co0 + cb;
+        if (g.ksplit > 1) {
+          float* w = g.ws + pix * g.Cout + co;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(w + j, __uint_as_float(vm[j]) + __uint_as_float(vc[j]));
+          continue;
+        }
+        const int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+        if (g.act == ACT_MASK) {
+          const uint4* mk = reinterpret_cast<const uint4*>(g.mask + pix * g.Cout + co);
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const uint4 m4 = __ldg(mk + j8);
+            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float sc = __ldg(g.scale + si + j8 * 8 + j);
+              v[j8 * 8 + j] = __bfloat162float(mb[j]) > 0.f ? v[j8 * 8 + j] * sc : 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = g.scale ? __ldg(g.scale + si + j) : 1.f;
+            const float sf = g.shift ? __ldg(g.shift + si + j) : 0.f;
+            v[j] = act_apply(fmaf(v[j], sc, sf), g.act);
+          }
+        }
+        if (g.out) {
+          __align__(16) __nv_bfloat16 hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
+          uint4* oh4 = reinterpret_cast<uint4*>(g.out + pix * g.Cout + co);
+          uint4* ol4 = reinterpret_cast<uint4*>(g.out + g.out_plane + pix * g.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
+            ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+          }
+        }
+        if (g.out_f32) {
+          float4* of = reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return nullptr; }
+  if (g.Cin % 64 || g.Cout % 128) { snprintf(err, errlen, "tc path needs Cin%%64==0, Cout%%128==0 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
+  TcMaps* m = new TcMaps();
+  memset(m, 0, sizeof(*m));
+  m->Wt = g.Wg < BM ? g.Wg : BM;
+  m->Ht = g.Hg < BM / m->Wt ? g.Hg : BM / m->Wt;
+  m->Nt = BM / (m->Wt * m->Ht);
+  m->BN = (g.Cout % 256 == 0) ? 256 : 128;
+  if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
+    snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
+    delete m; return nullptr;
+  }
+  // which views are used
+  bool used[4] = {false, false, false, false};
+  int max_tile = 0;
+  for (int p = 0; p < g.nphase; ++p)
+    for (int t = 0; t < g.phase[p].ntaps; ++t) {
+      const Tap& tp = g.taps[g.phase[p].tap_begin + t];
+      used[tp.view] = true;
+      if (tp.wtile > max_tile) max_tile = tp.wtile;
+    }
+  for (int v = 0; v < 4; ++v) {
+    if (!used[v]) continue;
+    const int vh = v >> 1, vw = v & 1;
+    const cuuint64_t Hv = (g.Hin - vh + g.sh - 1) / g.sh, Wv = (g.Win - vw + g.sw - 1) / g.sw;
+    cuuint64_t dims[5] = {(cuuint64_t)g.Cin, Wv, Hv, (cuuint64_t)g.n_img, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)g.sw * g.Cin * 2, (cuuint64_t)g.sh * g.Win * g.Cin * 2,
+                             (cuuint64_t)g.Hin * g.Win * g.Cin * 2, (cuuint64_t)g.a_plane * 2};
+    cuuint32_t box[5] = {BK, (cuuint32_t)m->Wt, (cuuint32_t)m->Ht, (cuuint32_t)m->Nt, 2};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    void* base = (void*)(g.a + ((long long)vh * g.Win + vw) * g.Cin);
+    CUresult r = enc(&m->a[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A view %d) failed: %d", v, (int)r); delete m; return nullptr; }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.Cin, (cuuint64_t)(max_tile + 1) * g.Cout, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.b_plane * 2};
+    cuuint32_t box[3] = {BK, (cuuint32_t)m->BN, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&m->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)g.b, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete m; return nullptr; }
+  }
+  return m;
+}
+
+void tc_free_maps(TcMaps* m) { delete m; }
+
+int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tapgemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
+    cudaFuncSetAttribute(tapgemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes);
+    attr_set = true;
+  }
+  const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
+  dim3 grid(tiles_m, g.Cout / maps->BN, g.nphase * g.ksplit);
+  if (maps->BN == 256)
+    tapgemm_tc_kernel<256><<<grid, kThreads, TcCfg<256>::kSmemBytes, st>>>(g, *maps);
+  else
+    tapgemm_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, st>>>(g, *maps);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ian

@@ -1,0 +1,38 @@
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) GPU; run by the driver on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def npe():
+    return importlib.import_module("neural-photo-editor_b200")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ian_simple_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def weights(golden):
+    from oracle import weights as ow
+    return ow.make_simple_weights(int(golden["weight_seed"]))
+
+
+@pytest.fixture(scope="session")
+def model(npe, weights):
+    """the product: API.IAN on cuda:0 through the C-ABI library (GPU tests only)."""
+    m = npe.IAN("IAN_simple.py", dnn=True, weights=weights, device=0)
+    yield m
+    m.close()

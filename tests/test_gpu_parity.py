@@ -1,0 +1,165 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through API.IAN -> ctypes -> C-ABI,
+against the float64 oracle's committed golden vectors and against the oracle run live on seeded inputs.
+
+Tolerances (float32 path; stated per BASELINE north_star "within 1e-4 max-abs"):
+  images  x_hat in [-1,1]           : max-abs <= 1e-4
+  latents z (|z| up to ~4)          : max-abs <= 2e-4
+  gradients / edited latents        : max-abs <= 1e-3 * max|ref| + 1e-7
+"""
+import numpy as np
+import pytest
+
+from oracle import ian_numpy as on
+
+pytestmark = pytest.mark.gpu
+
+X_TOL, Z_TOL = 1e-4, 2e-4
+
+
+def _x(golden):
+    return on.to_tanh(golden["images"].astype(np.float64)).astype(np.float32)
+
+
+@pytest.fixture(params=["tc", "simt"])
+def m(model, request):
+    model.set_path(request.param)
+    yield model
+    model.set_path("tc")
+
+
+def test_config1_single_image_reconstruction(m, golden):
+    """BASELINE config 1: CelebAValid[420] encode -> decode."""
+    x = _x(golden)[:1]
+    z = m.encode_images(x)
+    assert z.shape == (1, 100) and z.dtype == np.float32
+    assert np.abs(z - golden["mu"][:1]).max() <= Z_TOL
+    xh = m.sample_at(z)
+    assert xh.shape == (1, 3, 64, 64) and xh.dtype == np.float32
+    assert np.abs(xh - golden["xhat"][:1]).max() <= X_TOL + 5e-5   # z differs by <= Z_TOL from the oracle's
+
+
+def test_encode_golden(m, golden):
+    z = m.encode_images(_x(golden))
+    assert np.abs(z - golden["mu"]).max() <= Z_TOL
+
+
+def test_decode_golden(m, golden):
+    xh = m.sample_at(golden["z_rand"])
+    assert np.abs(xh - golden["xhat_rand"]).max() <= X_TOL
+    xh = m.sample_at(golden["mu"].astype(np.float32))
+    assert np.abs(xh - golden["xhat"]).max() <= X_TOL
+
+
+def test_reparameterised_sample(m, golden):
+    z = m.encode(_x(golden), eps=golden["eps"])
+    assert np.abs(z - golden["z_sample"]).max() <= 3 * Z_TOL        # exp(logsigma) amplifies
+
+
+def test_reconstruct_equals_encode_then_decode(m, golden):
+    x = _x(golden)
+    xh, z = m.reconstruct(x, return_z=True)
+    assert np.abs(z - golden["mu"]).max() <= Z_TOL
+    assert np.abs(xh - m.sample_at(z)).max() <= 2e-5
+
+
+def test_imgrad_reference_surface(m, golden):
+    c1, r1, c2, r2 = [float(v) for v in golden["boxes"][0]]       # NPE passes integral floats
+    z = golden["z_rand"][:2]
+    frame = np.broadcast_to(golden["rgb"][0].reshape(1, 3, 1, 1), (1, 3, 64, 64)).astype(np.float32).copy()
+    g = m.imgradRGB(c1, r1, c2, r2, frame, z)
+    ref = golden["g0_rgb"]
+    assert g.shape == z.shape and np.all(g[1] == 0)
+    assert np.abs(g - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7
+    g = m.imgrad(c1, r1, c2, r2, z)
+    ref = golden["g0_light"]
+    assert np.abs(g - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7
+    with pytest.raises(TypeError):
+        m.imgrad(1.5, 0, 4, 4, z)
+    with pytest.raises(TypeError):
+        m.imgrad(1, 0, 4, 4, z.astype(np.float64))
+    assert np.isnan(m.imgrad(5, 5, 5, 9, z)[0]).all()             # empty box -> mean of empty -> NaN
+
+
+def test_batched_grad_golden(m, golden):
+    g = m.grad(golden["z_rand"], golden["boxes"], golden["rgb"])
+    ref = golden["g_rgb"]
+    assert np.abs(g - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7
+    g = m.grad(golden["z_rand"], golden["boxes"], None)
+    ref = golden["g_light"]
+    assert np.abs(g - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-7
+    frames = np.broadcast_to(golden["rgb"].reshape(8, 3, 1, 1), (8, 3, 64, 64)).astype(np.float32).copy()
+    g2 = m.grad(golden["z_rand"], golden["boxes"], frames)
+    assert np.abs(g2 - golden["g_rgb"]).max() <= 1e-3 * np.abs(golden["g_rgb"]).max() + 1e-7
+
+
+def test_edit_loop_golden(m, golden):
+    z = m.edit_steps(golden["z_rand"][:4], golden["boxes"][:4], golden["rgb"][:4], n_steps=4, weight=0.05)
+    ref = golden["z_edit"]
+    moved = np.abs(ref - golden["z_rand"][:4]).max()
+    assert moved > 1e-3                                            # the loop did something
+    assert np.abs(z - ref).max() <= 1e-3 * moved + 1e-6
+
+
+def test_tc_matches_simt(model):
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, (5, 3, 64, 64)).astype(np.float32)
+    model.set_path("simt")
+    xs, zs = model.reconstruct(x, return_z=True)
+    model.set_path("tc")
+    xt, zt = model.reconstruct(x, return_z=True)
+    assert np.abs(zs - zt).max() <= 1e-4 and np.abs(xs - xt).max() <= 5e-5
+
+
+@pytest.mark.parametrize("n", [1, 3, 127, 130])
+def test_ragged_batches_and_sample_independence(model, n):
+    """inference BN keeps samples independent: any batch must equal its samples run alone."""
+    rng = np.random.default_rng(n)
+    x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
+    xh, z = model.reconstruct(x, return_z=True)
+    assert np.isfinite(xh).all() and np.isfinite(z).all()
+    pick = sorted({0, n // 2, n - 1})
+    xh1, z1 = model.reconstruct(x[pick], return_z=True)
+    assert np.abs(z[pick] - z1).max() <= 2e-5
+    assert np.abs(xh[pick] - xh1).max() <= 2e-5
+
+
+def test_full_size_batch256_properties(model, weights):
+    """BASELINE config 2 size: oracle on a 4-sample probe + independence / chunking invariants."""
+    rng = np.random.default_rng(1234)
+    x = rng.uniform(-1, 1, (256, 3, 64, 64)).astype(np.float32)
+    xh, z = model.reconstruct(x, return_z=True)
+    probe = [0, 85, 170, 255]
+    zr = on.simple_encode(weights, x[probe])
+    assert np.abs(z[probe] - zr).max() <= Z_TOL
+    xr = on.simple_decode(weights, z[probe])
+    assert np.abs(xh[probe] - xr).max() <= X_TOL
+    assert np.abs(xh).max() <= 1.0 and np.isfinite(xh).all()
+    # encode -> decode in two calls equals the fused call
+    assert np.abs(model.sample_at(model.encode_images(x)) - xh).max() <= 2e-5
+
+
+def test_batch_larger_than_plan_chunk(model):
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal((600, 100)).astype(np.float32)        # > 512-sample plan chunk
+    xh = model.sample_at(z)
+    assert np.abs(xh[[0, 511, 512, 599]] - model.sample_at(z[[0, 511, 512, 599]])).max() <= 2e-5
+
+
+def test_loader_rejects_bad_checkpoints(npe, weights):
+    bad = dict(weights)
+    bad["enc_conv2.W"] = bad["enc_conv2.W"][:, :64]
+    with pytest.raises(npe.IanError):
+        npe.IAN("IAN_simple.py", True, weights=bad)
+    missing = {k: v for k, v in weights.items() if k != "bnorm3.inv_std"}
+    with pytest.raises(npe.IanError):
+        npe.IAN("IAN_simple.py", True, weights=missing)
+    extra = dict(weights)
+    extra["not_a_layer.W"] = np.zeros((1,), np.float32)
+    with pytest.raises(npe.IanError):
+        npe.IAN("IAN_simple.py", True, weights=extra)
+
+
+def test_native_library_is_the_compute_path(model):
+    n0 = model.launch_count()
+    model.sample_at(np.zeros((2, 100), np.float32))
+    assert model.launch_count() - n0 >= 6                          # z_to_planes + 4 GEMM + dec_out
