@@ -166,7 +166,11 @@ def main():
     z = torch.empty(BATCH, 100, device=dev)
     xhat = torch.empty(BATCH, 3, 64, 64, device=dev)
     gathered = torch.empty(world * BATCH, 3, 64, 64, device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
+    work_stream = torch.cuda.Stream(device=dev)             # non-default stream: its handle is what the C-ABI takes
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+    assert stream != 0
+    torch.cuda.synchronize()
 
     def step():
         model.reconstruct_dev(x.data_ptr(), BATCH, z.data_ptr(), xhat.data_ptr(), stream)
