@@ -24,10 +24,10 @@ sys.path.insert(0, ROOT)
 BATCH = 256                      # per-GPU batch (BASELINE configs[1]); weak scaling over GPUs
 EDIT_BATCH, EDIT_STEPS = 128, 32  # BASELINE configs[3]
 GFLOP_PER_IMAGE = 2.5921488      # 1 296 074 400 MAC, encode -> decode
-# MACs per image executed by the tap-GEMM kernel (enc_conv2-4, enc_fc1, heads, l_dec_fc2, dec_conv1-3)
+# MACs per image executed by the tap-GEMM kernel (enc_conv2-4, enc_fc1, heads, l_dec_fc2, dec_conv1-3, dec_out)
 TAPGEMM_LAYERS = {"enc_conv2": 209715200, "enc_conv3": 209715200, "enc_conv4": 209715200, "enc_fc1": 16384000,
                   "enc_head": 200000, "l_dec_fc2": 1638400, "dec_conv1": 209715200, "dec_conv2": 209715200,
-                  "dec_conv3": 209715200}
+                  "dec_conv3": 209715200, "dec_out": 9830400}
 METRIC = "64x64 images/sec IAN encode->decode @ batch 256"
 
 
@@ -40,37 +40,69 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one
+    background `nvidia-smi -lms 20` process; samples are selected by wall-clock window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.path = "/tmp/ian_clocks_%d_%d.csv" % (os.getpid(), index)
+        self.f = open(self.path, "w")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.t0 = self.t1 = None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.05)
+    def start(self):
+        self.t0 = time.time()
+
+    def stop(self):
+        self.t1 = time.time()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        import datetime
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.f.close()
+        rows_all, rows_in = [], []
+        for line in open(self.path):
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                sm, mx, pw = float(c[1]), float(c[2]), float(c[3])
+            except Exception:
+                continue
+            row = (sm, mx, pw, c[4:8])
+            rows_all.append(row)
+            if self.t0 is not None and self.t0 - 0.01 <= ts <= (self.t1 or 1e18) + 0.01:
+                rows_in.append(row)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        rows = rows_in if rows_in else rows_all
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[0] for r in rows])) if rows else None,
+                "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "power_w_max": max(r[2] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(rows),
+                "window": "timed region" if rows_in else "whole run (timed region shorter than the sampling period)"}
 
 
 def cpu_restatement_rate(seconds_budget=15.0, batch=32, threads=None):
@@ -182,10 +214,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -196,8 +228,7 @@ def main():
     barrier()
     launches = model.launch_count() - l0
     ms = e0.elapsed_time(e1)
-    sampler.stop_flag = True
-    sampler.join()
+    sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -68,10 +68,10 @@ const char* kBnFields[] = {"beta", "gamma", "mean", "inv_std"};
 
 enum LayerId {
   L_ENC_CONV2 = 0, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3,
-  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_COUNT
+  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_DEC_OUT, L_COUNT
 };
 const char* kLayerNames[L_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "l_dec_fc2", "dec_conv1",
-                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2"};
+                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2", "dec_out"};
 
 struct DevWeights {           // one GEMM layer's B operand + epilogue vectors
   __nv_bfloat16* b = nullptr;
@@ -100,6 +100,7 @@ struct ian_handle {
   float* decout_wt = nullptr;  // [25][128][4]
   std::map<int, Plan*> plans;
   int max_chunk = 512;
+  int tc_merged = 0;           // IAN_TC_MERGED=1: single TMEM accumulator per tile (enables double buffering at BN=256)
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; };
   std::vector<Timed> timed[L_COUNT];
@@ -231,7 +232,7 @@ void set_io(TapGemm& g, const Planes& a, int n, int Hin, int Win, int Cin, int H
 
 int choose_ksplit(const TapGemm& g) {
   // fill ~one wave of 148 SMs when the output tile count is small; keep >= 4 K steps per CTA
-  const int bn = (g.Cout % 256 == 0) ? 256 : 128;
+  const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
   const int M = g.n_img * g.Hg * g.Wg;
   const int ctas = ((M + 127) / 128) * (g.Cout / bn) * g.nphase;
   int min_it = 1 << 30;
@@ -295,6 +296,10 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
   g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
 
+  // dec_out on the tensor-core path: 128 -> 3 channels padded to 16, tanh + NCHW float32 in the epilogue
+  set_io(g[L_DEC_OUT], pl->h3, n, 32, 32, 128, 32, 32, h->w[L_DEC_OUT], 64, 64); taps_deconv_s2(g[L_DEC_OUT]);
+  g[L_DEC_OUT].act = ACT_NONE; g[L_DEC_OUT].cout_real = 3;
+
   for (int l = 0; l < L_COUNT; ++l) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
@@ -327,8 +332,10 @@ int get_plan(ian_handle* h, int n, Plan** out) {
 }
 
 // ---- one tap-GEMM layer -------------------------------------------------------------------------
-int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
+int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st, float* out_nchw = nullptr) {
   TapGemm g = pl->g[l];
+  g.out_nchw = out_nchw;
+  g.tc_merged = h->tc_merged;
   ian_handle::Timed tm{};
   if (h->timing) {
     CUDA_TRY(h, cudaEventCreate(&tm.e0));
@@ -367,6 +374,7 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   int rc;
   for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  if (h->path == IAN_PATH_TC) return run_gemm(h, pl, L_DEC_OUT, st, xhat);
   LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
   return IAN_OK;
 }
@@ -556,6 +564,13 @@ int prepare_simple(ian_handle* h) {
   // dec_out: wt[ki*5+kj][ci][co(4)] = W[ci][co][ki][kj]
   {
     const auto& W = P(h, "dec_out.W").data;
+    // tensor-core form: B[k][co(16)][ci] = W[ci][co][k] for co < 3, zero padding above
+    B.assign((size_t)25 * 16 * 128, 0.f);
+    for (int ci = 0; ci < 128; ++ci)
+      for (int co = 0; co < 3; ++co)
+        for (int t = 0; t < 25; ++t) B[((size_t)t * 16 + co) * 128 + ci] = W[(ci * 3 + co) * 25 + t];
+    std::vector<float> ones16(16, 1.f);
+    if ((rc = upload_gemm_weights(h, L_DEC_OUT, B, 25, 16, 128, ones16, {})) != IAN_OK) return rc;
     std::vector<float> wt(25 * 128 * 4, 0.f);
     for (int ci = 0; ci < 128; ++ci)
       for (int co = 0; co < 3; ++co)
@@ -613,6 +628,7 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   }
   if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
+  if (const char* c = getenv("IAN_TC_MERGED")) h->tc_merged = atoi(c) != 0;
   *out = h;
   return IAN_OK;
 }

@@ -67,6 +67,10 @@ struct TapGemm {
   // finalize kernel applies the epilogue.
   int ksplit;
   float* ws;
+  // dec_out (tensor-core path, Cout padded to 16): tanh + float32 NCHW store of the first cout_real channels
+  float* out_nchw;
+  int cout_real;
+  int tc_merged;                // 1: cross terms accumulate into the main TMEM accumulator (frees a 2nd buffer)
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {
@@ -91,5 +95,6 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen);
 void tc_free_maps(TcMaps*);
 int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st);
 int launch_splitk_finalize(const TapGemm& g, cudaStream_t st);
+int tc_tile_width(const TcMaps* maps);
 
 }  // namespace ian

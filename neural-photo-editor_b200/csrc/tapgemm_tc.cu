@@ -1,6 +1,6 @@
 // tapgemm_tc.cu -- tcgen05 / TMEM / TMA implementation of the shifted-tap GEMM (see tapgemm.h).
 //
-// One CTA computes a 128 (pixels) x BN (output channels) tile of one output phase:
+// A persistent CTA (one per SM) computes 128 (pixels) x BN (output channels) tiles of the output phases:
 //   warp 0     : TMA producer.  Per K step (one tap x 64 input channels) two bulk-tensor loads:
 //                a 5-D box {64 ch, Wt, Ht, Nt, 2 planes} of the activation view the tap reads -- the
 //                tap shift is just a coordinate offset and the zero padding of the convolution is
@@ -12,7 +12,7 @@
 //                                         cross += A_lo * B_hi ;  cross += A_hi * B_lo
 //                in two separate TMEM accumulators (the 2^-9-smaller cross terms get their own
 //                accumulator so their rounding does not ride on the main sum's exponent).
-//   warps 2..5 : epilogue.  tcgen05.ld both accumulators, add, BatchNorm scale/shift + activation
+//   warps 2..9 : epilogue.  tcgen05.ld both accumulators, add, BatchNorm scale/shift + activation
 //                (or backward scale * ReLU-mask), re-split to bf16 hi/lo planes and store NHWC at
 //                the phase's output stride; or atomically add raw sums for split-K.
 // Pipeline: STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA -> tcgen05.commit).
@@ -35,15 +35,20 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                         // producer, MMA, 8 epilogue warps
 constexpr int kATileBytes = BM * BK * 2 * 2;            // hi + lo planes: 32 KB
 
-template <int BN> struct TcCfg {
+constexpr int kEpiWarps = 8;
+
+template <int BN, bool MERGED> struct TcCfg {
   static constexpr int kBTileBytes = BN * BK * 2 * 2;  // hi + lo
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (BN == 256) ? 2 : 3;
-  static constexpr int kTmemCols = 2 * BN;             // main + cross accumulators
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagesFit = (196 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kAccCols = MERGED ? BN : 2 * BN;        // TMEM columns of one accumulator buffer
+  static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = (kAccBufs * kAccCols <= 32) ? 32 : (kAccBufs * kAccCols <= 64) ? 64 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 256;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -54,6 +59,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -122,6 +130,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+template <int CH> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[CH]);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand descriptor (8-row x 128B atoms, SBO = 1024 B).
@@ -141,42 +160,66 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 // ---------------------------------------------------------------- kernel
+// Persistent, warp-specialised.  Work items w = blockIdx.x + i*gridDim.x over
+// (phase | k-split | n-tile | m-tile), longest phases first.  The smem ring and the TMEM accumulator
+// buffers run ACROSS work items: the producer prefetches the next tile's operands while the epilogue
+// of the current tile drains TMEM, and (when two accumulator buffers fit in the 512 TMEM columns) the
+// MMA warp starts the next tile while the epilogue warps are still converting/storing the previous one.
+struct WorkItem {
+  int phase, ks, n0, p0, q0, co0, it0, it1;
+};
+
 template <int BN>
+__device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& maps, int w) {
+  WorkItem wi;
+  const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
+  const int tiles_m = tiles_q * tiles_p * ((g.n_img + maps.Nt - 1) / maps.Nt);
+  const int tiles_n = g.Cout / BN;
+  const int per_phase = tiles_m * tiles_n * g.ksplit;
+  wi.phase = w / per_phase;
+  int r = w % per_phase;
+  int mt = r % tiles_m; r /= tiles_m;
+  const int nt = r % tiles_n; r /= tiles_n;
+  wi.ks = r;
+  const int qb = mt % tiles_q; mt /= tiles_q;
+  const int pb = mt % tiles_p; mt /= tiles_p;
+  wi.n0 = mt * maps.Nt; wi.p0 = pb * maps.Ht; wi.q0 = qb * maps.Wt;
+  wi.co0 = nt * BN;
+  const int total_it = g.phase[wi.phase].ntaps * (g.Cin / BK);
+  wi.it0 = (int)((long long)total_it * wi.ks / g.ksplit);
+  wi.it1 = (int)((long long)total_it * (wi.ks + 1) / g.ksplit);
+  return wi;
+}
+
+template <int BN, bool MERGED>
 __global__ void __launch_bounds__(kThreads, 1)
-tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps) {
-  using Cfg = TcCfg<BN>;
+tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
+  using Cfg = TcCfg<BN, MERGED>;
+  constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  // barriers: full[s] at +8s, empty[s] at +8(STAGES+s), tmem_full at +8*2*STAGES, tmem slot after
+  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * 2 * Cfg::kStages;
-  const uint32_t tmem_slot = tmem_full_bar + 8u;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  const uint32_t stage_smem = bar_base + 256u;       // per-epilogue-warp scale/shift staging: 8 x 64 floats
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_al + (tmem_slot - smem_base));
+  float* stage_ptr = reinterpret_cast<float*>(smem_al + (stage_smem - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- tile coordinates
-  const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
-  int mt = blockIdx.x;
-  const int qb = mt % tiles_q; mt /= tiles_q;
-  const int pb = mt % tiles_p; mt /= tiles_p;
-  const int n0 = mt * maps.Nt, p0 = pb * maps.Ht, q0 = qb * maps.Wt;
-  const int co0 = blockIdx.y * BN;
-  const int phase_idx = blockIdx.z / g.ksplit, ks = blockIdx.z % g.ksplit;
-  const Phase ph = g.phase[phase_idx];
-  const int nchunk = g.Cin / BK;
-  const int total_it = ph.ntaps * nchunk;
-  const int it0 = (int)((long long)total_it * ks / g.ksplit);
-  const int it1 = (int)((long long)total_it * (ks + 1) / g.ksplit);
-
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -184,120 +227,187 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nchunk = g.Cin / BK;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int it = it0; it < it1; ++it) {
-        const int i = it - it0;
-        const int s = i % Cfg::kStages;
-        const uint32_t par = (uint32_t)((i / Cfg::kStages) & 1);
-        const Tap tap = g.taps[ph.tap_begin + it / nchunk];
-        const int c0 = (it % nchunk) * BK;
-        mbar_wait(empty_bar(s), par ^ 1u);
-        mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        tma_load_5d(&maps.a[tap.view], full_bar(s), sa, c0, q0 + tap.dw, p0 + tap.dh, n0, 0);
-        tma_load_3d(&maps.b, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + co0, 0);
+      uint32_t i = 0;                                   // running K-step counter across work items
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const WorkItem wi = decode_work<BN>(g, maps, w);
+        const Phase ph = g.phase[wi.phase];
+        for (int it = wi.it0; it < wi.it1; ++it, ++i) {
+          const int s = i % S;
+          const uint32_t par = (i / S) & 1u;
+          const Tap tap = g.taps[ph.tap_begin + it / nchunk];
+          const int c0 = (it % nchunk) * BK;
+          mbar_wait(empty_bar(s), par ^ 1u);
+          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          tma_load_5d(&maps.a[tap.view], full_bar(s), sa, c0, wi.q0 + tap.dw, wi.p0 + tap.dh, wi.n0, 0);
+          tma_load_3d(&maps.b, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
-      const uint32_t acc_main = tmem_base, acc_cross = tmem_base + BN;
-      for (int it = it0; it < it1; ++it) {
-        const int i = it - it0;
-        const int s = i % Cfg::kStages;
-        const uint32_t par = (uint32_t)((i / Cfg::kStages) & 1);
-        mbar_wait(full_bar(s), par);
+      uint32_t i = 0, t = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
+        const WorkItem wi = decode_work<BN>(g, maps, w);
+        const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
+        const uint32_t acc_main = tmem_base + buf * Cfg::kAccCols;
+        const uint32_t acc_cross = MERGED ? acc_main : acc_main + BN;
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + BM * BK * 2);
-        const uint64_t b_hi = make_sw128_desc(sa + kATileBytes), b_lo = make_sw128_desc(sa + kATileBytes + BN * BK * 2);
+        for (int it = wi.it0; it < wi.it1; ++it, ++i) {
+          const int s = i % S;
+          const uint32_t par = (i / S) & 1u;
+          mbar_wait(full_bar(s), par);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + BM * BK * 2);
+          const uint64_t b_hi = make_sw128_desc(sa + kATileBytes), b_lo = make_sw128_desc(sa + kATileBytes + BN * BK * 2);
+          const bool first = (it == wi.it0);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ko = (uint64_t)(k * 2);       // 32 bytes per K=16 slice, in 16-byte units
-          const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-          umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-          umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes per K=16 slice, in 16-byte units
+            const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+            umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, MERGED ? 1u : acc);
+            umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar(s));                      // frees the smem stage when these MMAs retire
+        umma_commit(tfull_bar(buf));                    // accumulators of this work item complete
       }
-      umma_commit(tmem_full_bar);                       // accumulators complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    constexpr int CH = (BN >= 64) ? 32 : 16;            // columns per tcgen05.ld
+    constexpr int COLS_PER_WARP = (BN >= 64) ? BN / 2 : BN;
+    const int ew = warp - 2;
     const int lg = warp & 3;                            // TMEM lane group this warp may access
+    const int half = ew >> 2;                           // which half of the tile's columns
+    const bool has_cols = (BN >= 64) || half == 0;
+    float* my_stage = stage_ptr + ew * 64;
     const int ml = lg * 32 + lane;                      // tile row
     const int wl = ml % maps.Wt;
     const int hl = (ml / maps.Wt) % maps.Ht;
     const int nl = ml / (maps.Wt * maps.Ht);
-    const int n = n0 + nl, p = p0 + hl, q = q0 + wl;
-    const bool valid = n < g.n_img;
-    const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
-    const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
+      const WorkItem wi = decode_work<BN>(g, maps, w);
+      const Phase ph = g.phase[wi.phase];
+      const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
+      const int n = wi.n0 + nl, p = wi.p0 + hl, q = wi.q0 + wl;
+      const bool valid = n < g.n_img;
+      const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
+      const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
+      const uint32_t lane_addr = tmem_base + buf * Cfg::kAccCols + ((uint32_t)(lg * 32) << 16);
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
-    if (it1 > it0) {
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after();
+      if (has_cols && wi.it1 > wi.it0) {
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
-        uint32_t vm[32], vc[32];
-        tmem_ld32(lane_addr + cb, vm);
-        tmem_ld32(lane_addr + BN + cb, vc);
-        tmem_ld_wait();
-        if (!valid) continue;
-        const int co = co0 + cb;
-        if (g.ksplit > 1) {
-          float* w = g.ws + pix * g.Cout + co;
+        for (int cc = 0; cc < COLS_PER_WARP; cc += CH) {
+          const int cb = half * COLS_PER_WARP + cc;
+          const int co = wi.co0 + cb;
+          float v[CH];
+          __syncwarp();                                 // tcgen05.ld is .aligned: reconverge first
+          {
+            uint32_t vm[CH];
+            tmem_ld<CH>(lane_addr + cb, vm);
+            if (!MERGED) {
+              uint32_t vc[CH];
+              tmem_ld<CH>(lane_addr + BN + cb, vc);
+              tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(w + j, __uint_as_float(vm[j]) + __uint_as_float(vc[j]));
-          continue;
-        }
-        const int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
-        float v[32];
+              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+            } else {
+              tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
-        if (g.act == ACT_MASK) {
-          const uint4* mk = reinterpret_cast<const uint4*>(g.mask + pix * g.Cout + co);
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const uint4 m4 = __ldg(mk + j8);
-            const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float sc = __ldg(g.scale + si + j8 * 8 + j);
-              v[j8 * 8 + j] = __bfloat162float(mb[j]) > 0.f ? v[j8 * 8 + j] * sc : 0.f;
+              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]);
             }
           }
-        } else {
+          if (cc + CH >= COLS_PER_WARP) {               // last TMEM read of this work item: release the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          if (g.ksplit > 1) {
+            if (valid) {
+              float* wsp = g.ws + pix * g.Cout + co;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = g.scale ? __ldg(g.scale + si + j) : 1.f;
-            const float sf = g.shift ? __ldg(g.shift + si + j) : 0.f;
-            v[j] = act_apply(fmaf(v[j], sc, sf), g.act);
+              for (int j = 0; j < CH; ++j) atomicAdd(wsp + j, v[j]);
+            }
+            continue;
+          }
+          // per-channel scale/shift of this chunk: one coalesced load per warp, broadcast through smem
+          if (g.scale_pix_stride == 0) {
+            __syncwarp();
+            if (lane < CH) {
+              my_stage[lane] = g.scale ? __ldg(g.scale + co + lane) : 1.f;
+              my_stage[32 + lane] = g.shift ? __ldg(g.shift + co + lane) : 0.f;
+            }
+            __syncwarp();
+          }
+          if (valid) {
+            if (g.act == ACT_MASK) {
+              const int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
+              const uint4* mk = reinterpret_cast<const uint4*>(g.mask + pix * g.Cout + co);
+#pragma unroll
+              for (int j8 = 0; j8 < CH / 8; ++j8) {
+                const uint4 m4 = __ldg(mk + j8);
+                const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float sc = g.scale_pix_stride ? __ldg(g.scale + si + j8 * 8 + j) : my_stage[j8 * 8 + j];
+                  v[j8 * 8 + j] = __bfloat162float(mb[j]) > 0.f ? v[j8 * 8 + j] * sc : 0.f;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < CH / 4; ++j4) {
+                const float4 sc = *reinterpret_cast<const float4*>(my_stage + 4 * j4);
+                const float4 sf = *reinterpret_cast<const float4*>(my_stage + 32 + 4 * j4);
+                v[4 * j4 + 0] = act_apply(fmaf(v[4 * j4 + 0], sc.x, sf.x), g.act);
+                v[4 * j4 + 1] = act_apply(fmaf(v[4 * j4 + 1], sc.y, sf.y), g.act);
+                v[4 * j4 + 2] = act_apply(fmaf(v[4 * j4 + 2], sc.z, sf.z), g.act);
+                v[4 * j4 + 3] = act_apply(fmaf(v[4 * j4 + 3], sc.w, sf.w), g.act);
+              }
+            }
+            if (g.out) {
+              __align__(16) __nv_bfloat16 hi[CH], lo[CH];
+#pragma unroll
+              for (int j = 0; j < CH; ++j) split_bf16(v[j], hi[j], lo[j]);
+              uint4* oh4 = reinterpret_cast<uint4*>(g.out + pix * g.Cout + co);
+              uint4* ol4 = reinterpret_cast<uint4*>(g.out + g.out_plane + pix * g.Cout + co);
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
+                ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            }
+            if (g.out_f32) {
+              float4* of = reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (g.out_nchw) {                           // dec_out: tanh, float32 NCHW, first cout_real channels
+              float* o = g.out_nchw + ((long long)n * g.cout_real * g.Hout + oh) * g.Wout + ow;
+              const long long cs = (long long)g.Hout * g.Wout;
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (co + j < g.cout_real) o[(co + j) * cs] = tanhf(v[j]);
+            }
           }
         }
-        if (g.out) {
-          __align__(16) __nv_bfloat16 hi[32], lo[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
-          uint4* oh4 = reinterpret_cast<uint4*>(g.out + pix * g.Cout + co);
-          uint4* ol4 = reinterpret_cast<uint4*>(g.out + g.out_plane + pix * g.Cout + co);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
-            ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
-          }
-        }
-        if (g.out_f32) {
-          float4* of = reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
     }
   }
@@ -329,13 +439,13 @@ EncodeTiledFn get_encode_fn() {
 TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return nullptr; }
-  if (g.Cin % 64 || g.Cout % 128) { snprintf(err, errlen, "tc path needs Cin%%64==0, Cout%%128==0 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
+  if (g.Cin % 64 || (g.Cout % 128 && g.Cout != 16)) { snprintf(err, errlen, "tc path needs Cin%%64==0 and Cout%%128==0 or Cout==16 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
   TcMaps* m = new TcMaps();
   memset(m, 0, sizeof(*m));
   m->Wt = g.Wg < BM ? g.Wg : BM;
   m->Ht = g.Hg < BM / m->Wt ? g.Hg : BM / m->Wt;
   m->Nt = BM / (m->Wt * m->Ht);
-  m->BN = (g.Cout % 256 == 0) ? 256 : 128;
+  m->BN = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
   if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
     snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
     delete m; return nullptr;
@@ -379,20 +489,34 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
 
 void tc_free_maps(TcMaps* m) { delete m; }
 
-int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
+int tc_tile_width(const TcMaps* maps) { return maps->BN; }
+
+template <int BN, bool MERGED>
+static int launch_one(const TapGemm& g, const TcMaps* maps, int total_work, int grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, MERGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tapgemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes);
-    cudaFuncSetAttribute(tapgemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes);
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return -1;
     attr_set = true;
   }
-  const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
-  dim3 grid(tiles_m, g.Cout / maps->BN, g.nphase * g.ksplit);
-  if (maps->BN == 256)
-    tapgemm_tc_kernel<256><<<grid, kThreads, TcCfg<256>::kSmemBytes, st>>>(g, *maps);
-  else
-    tapgemm_tc_kernel<128><<<grid, kThreads, TcCfg<128>::kSmemBytes, st>>>(g, *maps);
+  tapgemm_tc_kernel<BN, MERGED><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
+  const int total_work = tiles_m * (g.Cout / maps->BN) * g.nphase * g.ksplit;
+  const int grid = total_work < num_sms ? total_work : num_sms;
+  if (maps->BN == 256) return g.tc_merged ? launch_one<256, true>(g, maps, total_work, grid, st) : launch_one<256, false>(g, maps, total_work, grid, st);
+  if (maps->BN == 128) return launch_one<128, false>(g, maps, total_work, grid, st);
+  return launch_one<16, false>(g, maps, total_work, grid, st);
 }
 
 }  // namespace ian
