@@ -1,0 +1,239 @@
+// decout_tc.cu -- dec_out (reference IAN_simple.py:171-181: DeconvLayer 128 -> 3 ch, 5x5, stride 2, tanh;
+// layers.py:436-483) as ONE dense tcgen05 GEMM plus an on-chip col2im, reading its input once.
+//
+// The output has only 3 channels, so the layer is bandwidth work: h3 is 512 KB/image, x_hat 48 KB.
+// Running it as a shifted-tap GEMM would re-stage every input pixel once per tap (25x).  Instead:
+//     T[pixel][tap*3+co] = sum_ci h3[pixel][ci] * W[ci][co][tap]          (M = pixels, K = 128, N = 75 -> 80)
+// has no shifts at all -- the A operand is the plain NHWC activation, one TMA box per 128 pixels -- and
+//     y[co, 2p+r, 2q+s] = sum_{d,e} T[(p+d, q+e)][tap(2+2d-r, 2+2e-s)*3 + co]       (<= 9 terms)
+// is a gather over a 3x3 pixel neighbourhood done from shared memory, followed by tanh and a coalesced
+// float32 NCHW store.  A work item is 4 input rows x 32 columns (= the 128-row MMA tile, rows p0-1..p0+2,
+// TMA zero-fills rows outside the image) and finishes the 4 output rows that depend only on it
+// (input rows p0, p0+1): 2x redundant GEMM work, which is free next to the saved traffic.
+//
+// Roles (persistent CTA, one per SM): warp 0 TMA producer (weights once, then an A ring), warp 1 MMA
+// issuer (3-pass bf16 split, main|cross accumulators, two TMEM buffers), warps 2-9 epilogue
+// (TMEM -> smem T tile -> col2im -> tanh -> store).
+#include <cstdio>
+#include <cstring>
+
+#include "edge.h"
+#include "tc_ptx.cuh"
+
+namespace ian {
+
+struct DecOutMaps {
+  CUtensorMap a;   // h3 planes (C=128, W=32, H=32, N, 2)
+  CUtensorMap b;   // weights  (C=128, 80 rows, 2)
+};
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int BN = 80;                       // 25 taps x 3 channels = 75, padded to a legal UMMA N
+constexpr int kAStage = 128 * 64 * 2 * 2;    // one K chunk of the A tile, hi+lo: 32 KB
+constexpr int kAStages = 3;
+constexpr int kBChunk = BN * 64 * 2 * 2;     // one K chunk of the weights, hi+lo: 20 KB
+constexpr int kTLd = 77;                     // T tile row pitch in floats (odd: conflict-free column access)
+constexpr int kTBytes = 128 * kTLd * 4;
+constexpr int kSmemBytes = 1024 + kAStages * kAStage + 2 * kBChunk + kTBytes + 256;
+constexpr int kItemsPerImage = 16;           // 32 input rows / 2 interior rows per item
+
+__global__ void __launch_bounds__(kThreads, 1)
+decout_tc_kernel(const __grid_constant__ DecOutMaps maps, float* __restrict__ xhat, const int n_img) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + kAStages * kAStage;
+  const uint32_t t_base = b_base + 2 * kBChunk;
+  const uint32_t bar_base = t_base + kTBytes;
+  float* Ts = reinterpret_cast<float*>(smem_al + (t_base - smem_base));
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kAStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kAStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kAStages + 2 + b); };
+  const uint32_t b_bar = bar_base + 8u * (2 * kAStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kAStages + 5);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_al + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = n_img * kItemsPerImage;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads / 32); }
+    mbar_init(b_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(b_bar, 2 * kBChunk);
+      tma_load_3d(&maps.b, b_bar, b_base, 0, 0, 0);
+      tma_load_3d(&maps.b, b_bar, b_base + kBChunk, 64, 0, 0);
+      uint32_t i = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int n = w / kItemsPerImage, p0 = (w % kItemsPerImage) * 2;
+        for (int c = 0; c < 2; ++c, ++i) {
+          const int s = i % kAStages;
+          mbar_wait(empty_bar(s), ((i / kAStages) & 1u) ^ 1u);
+          mbar_expect_tx(full_bar(s), kAStage);
+          tma_load_5d(&maps.a, full_bar(s), a_base + s * kAStage, c * 64, 0, p0 - 1, n, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
+      mbar_wait(b_bar, 0);
+      uint32_t i = 0, t = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++t) {
+        const uint32_t buf = t & 1u, use = t >> 1;
+        const uint32_t acc_main = tmem_base + buf * 256, acc_cross = acc_main + 128;
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        tc_fence_after();
+        for (int c = 0; c < 2; ++c, ++i) {
+          const int s = i % kAStages;
+          mbar_wait(full_bar(s), (i / kAStages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = a_base + s * kAStage, sb = b_base + c * kBChunk;
+          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + 128 * 64 * 2);
+          const uint64_t b_hi = make_sw128_desc(sb), b_lo = make_sw128_desc(sb + BN * 64 * 2);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ko = (uint64_t)(k * 2);
+            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+            umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> smem T tile -> col2im -> tanh -> NCHW store =====================
+    const int et = threadIdx.x - 64;                    // 0..255
+    const int ew = warp - 2;
+    const int lg = warp & 3;                            // TMEM lane group
+    const int half = ew >> 2;                           // columns [0,48) or [48,80)
+    const int row = lg * 32 + lane;                     // T tile row = pixel (pr*32 + q), pr = 0..3 <-> input row p0-1+pr
+    // output element handled in the col2im: out row ur (0..3) of the item, out col v (0..63)
+    const int ur = et >> 6, v = et & 63;
+    const int q = v >> 1, sx = v & 1, pr = 1 + (ur >> 1), ry = ur & 1;
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++t) {
+      const int n = w / kItemsPerImage, p0 = (w % kItemsPerImage) * 2;
+      const uint32_t buf = t & 1u, use = t >> 1;
+      const uint32_t lane_addr = tmem_base + buf * 256 + ((uint32_t)(lg * 32) << 16);
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after();
+      // this warp's columns: half 0 -> [0,48), half 1 -> [48,80)
+      const int c_begin = half ? 48 : 0, c_end = half ? 80 : 48;
+#pragma unroll 1
+      for (int cb = c_begin; cb < c_end; cb += 16) {
+        uint32_t vm[16], vc[16];
+        __syncwarp();
+        tmem_ld16(lane_addr + cb, vm);
+        tmem_ld16(lane_addr + 128 + cb, vc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (cb + j < 75) Ts[row * kTLd + cb + j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));       // TMEM buffer free: next item's MMAs may start
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // T tile complete (epilogue warps only)
+
+      // y[co, 2p+ry, 2q+sx] = sum_{d,e} T[(p+d, q+e)][(ki*5+kj)*3+co], ki = 2+2d-ry, kj = 2+2e-sx
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int d = -1; d <= 1; ++d) {
+        if (ry && d < 0) continue;
+        const int ki = 2 + 2 * d - ry;
+#pragma unroll
+        for (int e = -1; e <= 1; ++e) {
+          if (sx && e < 0) continue;
+          const int qq = q + e;
+          if (qq < 0 || qq > 31) continue;               // image border (rows are handled by TMA zero fill)
+          const int kj = 2 + 2 * e - sx;
+          const float* tp = Ts + ((pr + d) * 32 + qq) * kTLd + (ki * 5 + kj) * 3;
+          a0 += tp[0]; a1 += tp[1]; a2 += tp[2];
+        }
+      }
+      float* o = xhat + ((long long)n * 3 * 64 + (2 * p0 + ur)) * 64 + v;
+      o[0] = tanhf(a0);
+      o[4096] = tanhf(a1);
+      o[8192] = tanhf(a2);
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // T tile consumed: may be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,
+                              long long wt_plane, char* err, int errlen) {
+  tc::EncodeTiledFn enc = tc::get_encode_fn();
+  if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return nullptr; }
+  DecOutMaps* m = new DecOutMaps();
+  memset(m, 0, sizeof(*m));
+  {
+    cuuint64_t dims[5] = {128, 32, 32, (cuuint64_t)n_img, 2};
+    cuuint64_t strides[4] = {128 * 2, 32 * 128 * 2, 32 * 32 * 128 * 2, (cuuint64_t)h3_plane * 2};
+    cuuint32_t box[5] = {64, 32, 4, 1, 2};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&m->a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)h3, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(dec_out A) failed: %d", (int)r); delete m; return nullptr; }
+  }
+  {
+    cuuint64_t dims[3] = {128, BN, 2};
+    cuuint64_t strides[2] = {128 * 2, (cuuint64_t)wt_plane * 2};
+    cuuint32_t box[3] = {64, BN, 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&m->b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wt, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(dec_out B) failed: %d", (int)r); delete m; return nullptr; }
+  }
+  return m;
+}
+
+void decout_free_maps(DecOutMaps* m) { delete m; }
+
+int launch_dec_out_tc(const DecOutMaps* maps, float* xhat, int n, cudaStream_t st) {
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(decout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_set = true;
+  }
+  const int total = n * kItemsPerImage;
+  const int grid = total < num_sms ? total : num_sms;
+  decout_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*maps, xhat, n);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace ian

@@ -15,4 +15,10 @@ int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* 
                           long long plane, int n, cudaStream_t st);
 int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
                         __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st);
+// dec_out on the tensor-core path (decout_tc.cu)
+struct DecOutMaps;
+DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,
+                              long long wt_plane, char* err, int errlen);
+void decout_free_maps(DecOutMaps*);
+int launch_dec_out_tc(const DecOutMaps* maps, float* xhat, int n, cudaStream_t st);
 }  // namespace ian

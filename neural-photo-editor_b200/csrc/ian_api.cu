@@ -68,10 +68,11 @@ const char* kBnFields[] = {"beta", "gamma", "mean", "inv_std"};
 
 enum LayerId {
   L_ENC_CONV2 = 0, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3,
-  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_DEC_OUT, L_COUNT
+  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_COUNT,
+  T_CONV1 = L_COUNT, T_DEC_OUT, T_COUNT   // timing-only slots of the two edge kernels
 };
-const char* kLayerNames[L_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "l_dec_fc2", "dec_conv1",
-                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2", "dec_out"};
+const char* kLayerNames[T_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "l_dec_fc2", "dec_conv1",
+                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2", "enc_conv1", "dec_out"};
 
 struct DevWeights {           // one GEMM layer's B operand + epilogue vectors
   __nv_bfloat16* b = nullptr;
@@ -97,15 +98,16 @@ struct ian_handle {
   DevWeights w[L_COUNT];
   float* conv1_wt = nullptr;   // [75][128]
   float* conv1_b = nullptr;    // [128]
-  float* decout_wt = nullptr;  // [25][128][4]
+  float* decout_wt = nullptr;  // [25][128][4] fp32 (SIMT forward + brush backward)
+  __nv_bfloat16* decout_tc_wt = nullptr;   // [2][80][128] bf16 planes, row = tap*3+co (tensor-core forward)
   std::map<int, Plan*> plans;
   int max_chunk = 512;
   int tc_merged = 0;           // IAN_TC_MERGED=1: single TMEM accumulator per tile (enables double buffering at BN=256)
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; };
-  std::vector<Timed> timed[L_COUNT];
-  double time_ms[L_COUNT] = {0};
-  long long time_cnt[L_COUNT] = {0};
+  std::vector<Timed> timed[T_COUNT];
+  double time_ms[T_COUNT] = {0};
+  long long time_cnt[T_COUNT] = {0};
 };
 
 namespace {
@@ -146,6 +148,7 @@ struct Plan {
   int32_t* boxes = nullptr;
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
+  DecOutMaps* decout_maps = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -296,10 +299,6 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
   g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
 
-  // dec_out on the tensor-core path: 128 -> 3 channels padded to 16, tanh + NCHW float32 in the epilogue
-  set_io(g[L_DEC_OUT], pl->h3, n, 32, 32, 128, 32, 32, h->w[L_DEC_OUT], 64, 64); taps_deconv_s2(g[L_DEC_OUT]);
-  g[L_DEC_OUT].act = ACT_NONE; g[L_DEC_OUT].cout_real = 3;
-
   for (int l = 0; l < L_COUNT; ++l) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
@@ -310,6 +309,11 @@ int build_plan(ian_handle* h, int n, Plan** out) {
     }
   }
   // the split-K finalize of dz writes its result in place (ws == out_f32): finalize reads then writes
+  {
+    char err[256] = {0};
+    pl->decout_maps = decout_build_maps(pl->h3.p, pl->h3.plane, n, h->decout_tc_wt, 80 * 128, err, sizeof(err));
+    if (!pl->decout_maps) return fail(h, IAN_ERR_CUDA, "dec_out: %s", err);
+  }
   *out = pl;
   return IAN_OK;
 }
@@ -317,6 +321,7 @@ int build_plan(ian_handle* h, int n, Plan** out) {
 void free_plan(Plan* pl) {
   for (void* p : pl->allocs) cudaFree(p);
   for (int l = 0; l < L_COUNT; ++l) tc_free_maps(pl->maps[l]);
+  decout_free_maps(pl->decout_maps);
   delete pl;
 }
 
@@ -332,9 +337,19 @@ int get_plan(ian_handle* h, int n, Plan** out) {
 }
 
 // ---- one tap-GEMM layer -------------------------------------------------------------------------
-int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st, float* out_nchw = nullptr) {
+// CUDA-event pair around one kernel when layer timing is on
+struct ScopedTimer {
+  ian_handle* h; int slot; cudaStream_t st; ian_handle::Timed tm{}; bool on;
+  ScopedTimer(ian_handle* h_, int slot_, cudaStream_t st_) : h(h_), slot(slot_), st(st_), on(h_->timing) {
+    if (on) { cudaEventCreate(&tm.e0); cudaEventCreate(&tm.e1); cudaEventRecord(tm.e0, st); }
+  }
+  ~ScopedTimer() {
+    if (on) { cudaEventRecord(tm.e1, st); h->timed[slot].push_back(tm); }
+  }
+};
+
+int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
-  g.out_nchw = out_nchw;
   g.tc_merged = h->tc_merged;
   ian_handle::Timed tm{};
   if (h->timing) {
@@ -361,7 +376,10 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st, float* out_nchw = 
 
 int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float* z, cudaStream_t st) {
   const int n = pl->n;
-  LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+  {
+    ScopedTimer tm(h, T_CONV1, st);
+    LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+  }
   int rc;
   for (int l : {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
@@ -374,8 +392,11 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   int rc;
   for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-  if (h->path == IAN_PATH_TC) return run_gemm(h, pl, L_DEC_OUT, st, xhat);
-  LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
+  ScopedTimer tm(h, T_DEC_OUT, st);
+  if (h->path == IAN_PATH_TC)
+    LAUNCH_TRY(h, launch_dec_out_tc(pl->decout_maps, xhat, pl->n, st));
+  else
+    LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
   return IAN_OK;
 }
 
@@ -564,13 +585,20 @@ int prepare_simple(ian_handle* h) {
   // dec_out: wt[ki*5+kj][ci][co(4)] = W[ci][co][ki][kj]
   {
     const auto& W = P(h, "dec_out.W").data;
-    // tensor-core form: B[k][co(16)][ci] = W[ci][co][k] for co < 3, zero padding above
-    B.assign((size_t)25 * 16 * 128, 0.f);
-    for (int ci = 0; ci < 128; ++ci)
-      for (int co = 0; co < 3; ++co)
-        for (int t = 0; t < 25; ++t) B[((size_t)t * 16 + co) * 128 + ci] = W[(ci * 3 + co) * 25 + t];
-    std::vector<float> ones16(16, 1.f);
-    if ((rc = upload_gemm_weights(h, L_DEC_OUT, B, 25, 16, 128, ones16, {})) != IAN_OK) return rc;
+    // tensor-core form (decout_tc.cu): rows j = tap*3+co (75, padded to 80), K-major over ci; bf16 hi|lo planes
+    {
+      std::vector<uint16_t> planes(2 * 80 * 128, 0);
+      for (int ci = 0; ci < 128; ++ci)
+        for (int co = 0; co < 3; ++co)
+          for (int t = 0; t < 25; ++t) {
+            const float w = W[(ci * 3 + co) * 25 + t];
+            const uint16_t hi = f2bf(w);
+            planes[(t * 3 + co) * 128 + ci] = hi;
+            planes[80 * 128 + (t * 3 + co) * 128 + ci] = f2bf(w - bf2f(hi));
+          }
+      CUDA_TRY(h, cudaMalloc((void**)&h->decout_tc_wt, planes.size() * 2));
+      CUDA_TRY(h, cudaMemcpy(h->decout_tc_wt, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    }
     std::vector<float> wt(25 * 128 * 4, 0.f);
     for (int ci = 0; ci < 128; ++ci)
       for (int co = 0; co < 3; ++co)
@@ -686,7 +714,7 @@ int ian_destroy(ian_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
-  cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt);
+  cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   cudaStreamDestroy(h->stream);
   delete h;
@@ -713,7 +741,7 @@ int ian_set_layer_timing(ian_handle* h, int enable) {
 double ian_layer_time_ms(ian_handle* h, const char* layer_name, int reset) {
   if (!h || !layer_name) return -1.0;
   DeviceGuard dg(h->device);
-  for (int l = 0; l < L_COUNT; ++l) {
+  for (int l = 0; l < T_COUNT; ++l) {
     if (strcmp(kLayerNames[l], layer_name)) continue;
     for (auto& t : h->timed[l]) {
       float ms = 0.f;

@@ -67,9 +67,6 @@ struct TapGemm {
   // finalize kernel applies the epilogue.
   int ksplit;
   float* ws;
-  // dec_out (tensor-core path, Cout padded to 16): tanh + float32 NCHW store of the first cout_real channels
-  float* out_nchw;
-  int cout_real;
   int tc_merged;                // 1: cross terms accumulate into the main TMEM accumulator (frees a 2nd buffer)
 };
 
