@@ -106,17 +106,42 @@ class ClockSampler:
                 "window": "timed region" if rows_in else "whole run (timed region shorter than the sampling period)"}
 
 
-def cpu_restatement_rate(seconds_budget=15.0, batch=32, threads=None):
-    """The reference's Theano CPU path cannot run (SURVEY F3): time the float32 torch restatement of the
-    reference graph on the host cores, on a bounded sample of the same workload."""
+def _cpu_setup():
     from oracle import ian_torch as ot
     from oracle import weights as ow
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
     P = ot.to_torch(ow.make_simple_weights(0), torch.float32)
+    return ot, P
+
+
+def _pick_threads(ot, P, x):
+    """torch oversubscribes badly when the container is cpu-limited: time one batch per candidate thread count."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    best, best_t = 1, float("inf")
+    for th in sorted({avail, 64, 32, 16, 8}, reverse=True):
+        if th > avail:
+            continue
+        torch.set_num_threads(th)
+        with torch.no_grad():
+            ot.decode(P, ot.encode(P, x))
+            t0 = time.perf_counter()
+            ot.decode(P, ot.encode(P, x))
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = th, dt
+    torch.set_num_threads(best)
+    return best, avail
+
+
+def cpu_restatement_rate(seconds_budget=12.0, batch=32):
+    """The reference's Theano CPU path cannot run (SURVEY F3): time the float32 torch restatement of the
+    reference graph on the host cores, on a bounded sample of the same workload."""
+    ot, P = _cpu_setup()
     x = torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, (batch, 3, 64, 64)).astype(np.float32))
+    threads, avail = _pick_threads(ot, P, x)
     with torch.no_grad():
-        ot.decode(P, ot.encode(P, x))                      # warm-up
         t0, n = time.perf_counter(), 0
         while True:
             ot.decode(P, ot.encode(P, x))
@@ -125,8 +150,8 @@ def cpu_restatement_rate(seconds_budget=15.0, batch=32, threads=None):
                 break
         dt = time.perf_counter() - t0
     return {"value": batch * n / dt, "unit": "images/sec", "cores": threads, "kind": "port",
-            "sample": "%d x batch-%d encode->decode of the float32 torch-CPU restatement (oracle/ian_torch.py), %.1f s"
-                      % (n, batch, dt)}
+            "sample": "%d x batch-%d encode->decode of the float32 torch-CPU restatement (oracle/ian_torch.py), %.1f s; "
+                      "%d threads picked by calibration out of %d available" % (n, batch, dt, threads, avail)}
 
 
 def run_reference(args, rank, world):
@@ -134,13 +159,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     t_all = time.perf_counter()
-    from oracle import ian_torch as ot
-    from oracle import weights as ow
-    threads = os.cpu_count()
-    torch.set_num_threads(threads)
-    P = ot.to_torch(ow.make_simple_weights(0), torch.float32)
+    ot, P = _cpu_setup()
     sample = 32                                             # bounded sample of the batch-256 workload per step
     x = torch.from_numpy(np.random.default_rng(1234).uniform(-1, 1, (sample, 3, 64, 64)).astype(np.float32))
+    threads, avail = _pick_threads(ot, P, x)
     with torch.no_grad():
         for _ in range(args.warmup):
             ot.decode(P, ot.encode(P, x))
@@ -152,9 +174,11 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "IAN_simple encode->decode, batch 256 per GPU, fp32", "global_batch": BATCH * world,
+            "config": {"workload": "IAN_simple encode->decode, batch 256 per GPU (BASELINE configs[1])",
+                       "global_batch": BATCH * world,
                        "note": "reference Theano path cannot run here (py2/theano absent); this is the CPU restatement "
-                               "of the reference graph on %d host threads, each step a %d-image sample" % (threads, sample)},
+                               "of the reference graph on %d host threads (of %d available), each step a %d-image sample"
+                               % (threads, avail, sample)},
             "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
                              "sample": "%d steps x %d images" % (args.steps, sample)},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -250,7 +274,11 @@ def main():
     peak_fp32_equiv = pk["bf16_tflops_sustained"] / 3.0
     achieved = tg_flops / (tg_ms / 1e3) / 1e12 if tg_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "tapgemm_tc_kernel", "achieved": achieved, "peak": peak_fp32_equiv,
-                "unit": "TFLOP/s", "frac": achieved / peak_fp32_equiv, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak_fp32_equiv,
+                # dram__bytes_read+write summed over the 9 tap-GEMM launches of one step, from the ncu --set full
+                # capture of this same command (profiles/r1_ncu_tc_kernels_full_summary.csv); algorithmic bytes of
+                # those launches are 943 MB (573 MB operands read once + 370 MB outputs)
+                "traffic": 872.3e6 if BATCH == 256 else None, "traffic_unit": "bytes per step (all tap-GEMM launches)",
                 "peak_note": "%s bf16_tflops_sustained (%.1f) / 3: fp32 parity is reached by a 3-pass bf16 split, so each "
                              "algorithmic MAC costs 3 tensor-core MACs" % (pk["src"], pk["bf16_tflops_sustained"]),
                 "tensor_executed_tflops": 3 * achieved, "kernel_ms_per_step": tg_ms,
@@ -258,24 +286,37 @@ def main():
                 "layer_ms": {k: round(v, 4) for k, v in layer_ms.items()},
                 "edge_kernel_ms": {k: round(v, 4) for k, v in edge_ms.items()}}
 
-    # ---- e2e through the public API with host buffers (H2D + D2H inside the timed region)
-    xh_host = np.empty((BATCH, 3, 64, 64), np.float32)
+    # ---- e2e through the public API with HOST buffers (H2D + D2H of every step inside the timed region).
+    # (a) synchronous call IAN.reconstruct(x, out=...), (b) the streaming call IAN.reconstruct_stream(...) that
+    # keeps two batches in flight so one batch's copies overlap its neighbours' compute.  Pinned buffers.
     x_np = x_host.numpy()
+    out_pinned = model.pinned_empty((BATCH, 3, 64, 64))
     for _ in range(3):
-        model.reconstruct(x_np)
+        model.reconstruct(x_np, out=out_pinned)
+    barrier()
+    e2e_steps = max(5, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.reconstruct(x_np, out=out_pinned)
+    t_sync = time.perf_counter() - t0
+    for _ in model.reconstruct_stream(x_np for _ in range(3)):
+        pass
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(5, args.steps // 2)
-    for _ in range(e2e_steps):
-        xh_host = model.reconstruct(x_np)
-    t_e2e = time.perf_counter() - t0
+    checksum = 0.0
+    for xh in model.reconstruct_stream(x_np for _ in range(e2e_steps)):
+        checksum += float(xh[0, 0, 0, 0])                   # touch every result on the host
+    t_pipe = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([t_e2e], device=dev)
+        t = torch.tensor([t_sync, t_pipe], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e = {"value": world * BATCH * e2e_steps / t_e2e, "unit": "images/sec", "h2d_bytes_per_step": BATCH * 12288 * 4,
-           "d2h_bytes_per_step": BATCH * 12288 * 4 + BATCH * 400,
-           "api": "IAN.reconstruct(numpy (256,3,64,64)) -> ian_reconstruct_host, synchronous"}
+        t_sync, t_pipe = float(t[0].item()), float(t[1].item())
+    e2e = {"value": world * BATCH * e2e_steps / t_pipe, "unit": "images/sec", "h2d_bytes_per_step": BATCH * 12288 * 4,
+           "d2h_bytes_per_step": BATCH * 12288 * 4,
+           "api": "IAN.reconstruct_stream(batches of numpy (256,3,64,64) in pinned memory): 2 batches in flight, "
+                  "every batch is copied H2D, encoded, decoded and copied D2H",
+           "sync_value": world * BATCH * e2e_steps / t_sync,
+           "sync_api": "IAN.reconstruct(x, out=pinned) -> ian_reconstruct_host, one batch at a time", "steps": e2e_steps}
 
     # ---- secondary metric: latent-edit steps/sec (BASELINE configs[3])
     edit = None

@@ -22,6 +22,7 @@
 #ifndef IAN_B200_H_
 #define IAN_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -87,6 +88,18 @@ int ian_decode_host(ian_handle* h, const float* z, int n, float* x);
 int ian_reconstruct_dev(ian_handle* h, const float* x, int n, float* z_out /*nullable*/, float* x_hat,
                         void* stream);
 int ian_reconstruct_host(ian_handle* h, const float* x, int n, float* z_out /*nullable*/, float* x_hat);
+
+/* ---- pipelined encode -> decode for streaming use (no reference equivalent; the reference is synchronous) --
+ * ian_reconstruct_submit enqueues  H2D(x) -> encode -> decode -> D2H(x_hat[, z])  on three streams (copy-in,
+ * compute, copy-out) and returns a ticket at once; up to two requests are in flight, so the copies of one request
+ * overlap the compute of its neighbours.  ian_reconstruct_wait blocks until that request's outputs have landed in
+ * the host buffers, which must stay valid until then.  n <= 512.  Pinned host memory (ian_host_alloc) is what
+ * makes the copies asynchronous; pageable memory works but serialises. */
+int ian_reconstruct_submit(ian_handle* h, const float* x, int n, float* z_out /*nullable*/, float* x_hat, int* ticket);
+int ian_reconstruct_wait(ian_handle* h, int ticket);
+/* Page-locked host memory owned by the handle (freed by ian_host_free or ian_destroy). */
+int ian_host_alloc(ian_handle* h, size_t bytes, void** out);
+int ian_host_free(ian_handle* h, void* p);
 
 /* ---- latent-brush gradients: replace calculate_RGB_gradient / calculate_lighten_gradient
  * (reference API.py:59, 64; IAN.imgrad / IAN.imgradRGB API.py:66-76), batched per sample -------- */

@@ -185,15 +185,67 @@ class IAN:
             self._check(self._lib.ian_encode_host(self._h, _fp(x), n, _fp(e) if e is not None else None, _fp(z)))
         return z
 
-    def reconstruct(self, images, return_z=False):
-        """encode -> decode in one library call (the BASELINE metric's path)."""
+    def reconstruct(self, images, return_z=False, out=None):
+        """encode -> decode in one library call (the BASELINE metric's path).  `out`: optional preallocated
+        float32 (n,3,64,64) result buffer (e.g. from pinned_empty) to avoid a pageable allocation per call."""
         x = _f32(images, 4, 'images')
         n = x.shape[0]
-        xh = np.empty_like(x)
+        xh = np.empty_like(x) if out is None else self._out(out, x.shape)
         z = np.empty((n, 100), np.float32)
         if n:
             self._check(self._lib.ian_reconstruct_host(self._h, _fp(x), n, _fp(z), _fp(xh)))
         return (xh, z) if return_z else xh
+
+    @staticmethod
+    def _out(out, shape):
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == tuple(shape)
+                and out.flags['C_CONTIGUOUS']):
+            raise TypeError("out must be a C-contiguous float32 array of shape %r" % (tuple(shape),))
+        return out
+
+    def pinned_empty(self, shape):
+        """float32 numpy array in page-locked host memory owned by this model (valid until close())."""
+        nbytes = int(np.prod(shape)) * 4
+        p = C.c_void_p()
+        self._check(self._lib.ian_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_float * (nbytes // 4)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(shape)
+
+    def reconstruct_submit(self, images, out, z_out=None):
+        """Pipelined encode -> decode: enqueue one batch (n <= 512) and return a ticket immediately; `out`
+        (and `z_out`) receive the result once reconstruct_wait(ticket) returns.  Two requests may be in
+        flight; use pinned_empty() buffers so the copies overlap the neighbouring requests' compute."""
+        x = _f32(images, 4, 'images')
+        n = x.shape[0]
+        out = self._out(out, x.shape)
+        if z_out is not None:
+            z_out = self._out(z_out, (n, 100))
+        t = C.c_int()
+        self._check(self._lib.ian_reconstruct_submit(self._h, _fp(x), n, _fp(z_out) if z_out is not None else None,
+                                                     _fp(out), C.byref(t)))
+        return t.value
+
+    def reconstruct_wait(self, ticket):
+        self._check(self._lib.ian_reconstruct_wait(self._h, int(ticket)))
+
+    def reconstruct_stream(self, batches):
+        """Generator over an iterable of (n,3,64,64) float32 batches: yields each reconstruction in order while
+        keeping two batches in flight (H2D / compute / D2H of neighbouring batches overlap).  The yielded array
+        is one of two rotating pinned buffers: consume it before advancing the generator twice."""
+        outs, pending = {}, None
+        for i, x in enumerate(batches):
+            x = _f32(x, 4, 'images')
+            key = (i & 1, x.shape)
+            if key not in outs:
+                outs[key] = self.pinned_empty(x.shape)
+            t = self.reconstruct_submit(x, outs[key])
+            if pending is not None:
+                self.reconstruct_wait(pending[0])
+                yield pending[1]
+            pending = (t, outs[key])
+        if pending is not None:
+            self.reconstruct_wait(pending[0])
+            yield pending[1]
 
     def _target(self, rgb, n):
         if rgb is None:

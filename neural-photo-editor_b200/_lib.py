@@ -32,6 +32,10 @@ SIGNATURES = {
     "ian_decode_host": (C.c_int, [_H, _F, C.c_int, _F]),
     "ian_reconstruct_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ian_reconstruct_host": (C.c_int, [_H, _F, C.c_int, _F, _F]),
+    "ian_reconstruct_submit": (C.c_int, [_H, _F, C.c_int, _F, _F, C.POINTER(C.c_int)]),
+    "ian_reconstruct_wait": (C.c_int, [_H, C.c_int]),
+    "ian_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ian_host_free": (C.c_int, [_H, C.c_void_p]),
     "ian_grad_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ian_grad_host": (C.c_int, [_H, _F, _I, _F, C.c_int, C.c_int, _F]),
     "ian_edit_loop_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -92,6 +92,9 @@ struct ian_handle {
   int path = IAN_PATH_TC;
   bool finalized = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined host API
+  std::vector<void*> host_allocs;
+  long long tickets = 0;
   std::string err;
   int64_t launches = 0;
   std::map<std::string, HostParam> params;
@@ -149,6 +152,9 @@ struct Plan {
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
   DecOutMaps* decout_maps = nullptr;
+  // pipelined host API: double-buffered boundary tensors + events (allocated on first use)
+  float *sx[2] = {nullptr, nullptr}, *sz[2] = {nullptr, nullptr}, *sxh[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
 };
 
@@ -320,6 +326,11 @@ int build_plan(ian_handle* h, int n, Plan** out) {
 
 void free_plan(Plan* pl) {
   for (void* p : pl->allocs) cudaFree(p);
+  for (int s = 0; s < 2; ++s) {
+    if (pl->ev_h2d[s]) cudaEventDestroy(pl->ev_h2d[s]);
+    if (pl->ev_comp[s]) cudaEventDestroy(pl->ev_comp[s]);
+    if (pl->ev_d2h[s]) cudaEventDestroy(pl->ev_d2h[s]);
+  }
   for (int l = 0; l < L_COUNT; ++l) tc_free_maps(pl->maps[l]);
   decout_free_maps(pl->decout_maps);
   delete pl;
@@ -650,7 +661,9 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   h->device = device;
   h->model_kind = model_kind;
   DeviceGuard dg(device);
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(nullptr, IAN_ERR_CUDA, "cudaStreamCreate failed");
   }
@@ -712,11 +725,16 @@ int ian_destroy(ian_handle* h) {
   if (!h) return IAN_OK;
   DeviceGuard dg(h->device);
   cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->h2d_stream);
+  cudaStreamSynchronize(h->d2h_stream);
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
   cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (void* p : h->host_allocs) cudaFreeHost(p);
   cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->h2d_stream);
+  cudaStreamDestroy(h->d2h_stream);
   delete h;
   return IAN_OK;
 }
@@ -938,6 +956,77 @@ int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const floa
   });
   if (rc != IAN_OK) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+
+// ---- pipelined host API -----------------------------------------------------------------------------
+int ian_host_alloc(ian_handle* h, size_t bytes, void** out) {
+  if (!h || !out || bytes == 0) return fail(h, IAN_ERR_INVALID, "bad argument");
+  DeviceGuard dg(h->device);
+  void* p = nullptr;
+  CUDA_TRY(h, cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  h->host_allocs.push_back(p);
+  *out = p;
+  return IAN_OK;
+}
+
+int ian_host_free(ian_handle* h, void* p) {
+  if (!h || !p) return IAN_ERR_INVALID;
+  for (size_t i = 0; i < h->host_allocs.size(); ++i)
+    if (h->host_allocs[i] == p) {
+      h->host_allocs.erase(h->host_allocs.begin() + i);
+      DeviceGuard dg(h->device);
+      CUDA_TRY(h, cudaFreeHost(p));
+      return IAN_OK;
+    }
+  return fail(h, IAN_ERR_INVALID, "pointer was not allocated by ian_host_alloc");
+}
+
+int ian_reconstruct_submit(ian_handle* h, const float* x, int n, float* z_out, float* x_hat, int* ticket) {
+  int rc = check_ready(h, n, x, x_hat);
+  if (rc != IAN_OK) return rc;
+  if (!ticket) return fail(h, IAN_ERR_INVALID, "ticket is NULL");
+  if (n > h->max_chunk) return fail(h, IAN_ERR_INVALID, "pipelined calls take at most %d images (got %d)", h->max_chunk, n);
+  DeviceGuard dg(h->device);
+  Plan* pl = nullptr;
+  if ((rc = get_plan(h, n, &pl)) != IAN_OK) return rc;
+  const int s = (int)(h->tickets & 1);
+  if (!pl->sx[s]) {
+    for (int b = 0; b < 2; ++b) {
+      if ((rc = alloc_buf(h, pl, pl->sx[b], (long long)n * 12288)) != IAN_OK) return rc;
+      if ((rc = alloc_buf(h, pl, pl->sz[b], (long long)n * 100)) != IAN_OK) return rc;
+      if ((rc = alloc_buf(h, pl, pl->sxh[b], (long long)n * 12288)) != IAN_OK) return rc;
+      CUDA_TRY(h, cudaEventCreateWithFlags(&pl->ev_h2d[b], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&pl->ev_comp[b], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&pl->ev_d2h[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));     // the memsets of the new buffers
+  } else {
+    CUDA_TRY(h, cudaEventSynchronize(pl->ev_d2h[s]));  // the request that used this slot two submits ago is done
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(pl->sx[s], x, (size_t)n * 12288 * 4, cudaMemcpyHostToDevice, h->h2d_stream));
+  CUDA_TRY(h, cudaEventRecord(pl->ev_h2d[s], h->h2d_stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, pl->ev_h2d[s], 0));
+  if ((rc = run_encode(h, pl, pl->sx[s], nullptr, pl->sz[s], h->stream)) != IAN_OK) return rc;
+  if ((rc = run_decode_from_planes(h, pl, pl->sxh[s], h->stream)) != IAN_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(pl->ev_comp[s], h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, pl->ev_comp[s], 0));
+  CUDA_TRY(h, cudaMemcpyAsync(x_hat, pl->sxh[s], (size_t)n * 12288 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
+  if (z_out) CUDA_TRY(h, cudaMemcpyAsync(z_out, pl->sz[s], (size_t)n * 400, cudaMemcpyDeviceToHost, h->d2h_stream));
+  CUDA_TRY(h, cudaEventRecord(pl->ev_d2h[s], h->d2h_stream));
+  *ticket = (int)(((h->tickets & 1) << 16) | (unsigned)n);   // slot parity in bit 16, batch size in the low bits
+  h->tickets += 1;
+  return IAN_OK;
+}
+
+int ian_reconstruct_wait(ian_handle* h, int ticket) {
+  if (!h) return IAN_ERR_INVALID;
+  const int n = ticket & 0xffff, s = (ticket >> 16) & 1;
+  auto it = h->plans.find(n);
+  if (it == h->plans.end() || !it->second->ev_d2h[s]) return fail(h, IAN_ERR_INVALID, "unknown ticket %d", ticket);
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaEventSynchronize(it->second->ev_d2h[s]));
   return IAN_OK;
 }
 

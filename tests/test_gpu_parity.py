@@ -158,6 +158,23 @@ def test_batch_larger_than_plan_chunk(model):
     assert np.abs(xh[[0, 511, 512, 599]] - model.sample_at(z[[0, 511, 512, 599]])).max() <= 2e-5
 
 
+def test_pipelined_stream_matches_sync(model):
+    rng = np.random.default_rng(9)
+    batches = [rng.uniform(-1, 1, (5, 3, 64, 64)).astype(np.float32) for _ in range(5)]
+    want = [model.reconstruct(b) for b in batches]
+    got = [xh.copy() for xh in model.reconstruct_stream(iter(batches))]
+    assert len(got) == 5
+    for a, b in zip(want, got):
+        assert np.abs(a - b).max() <= 2e-5
+    out = model.pinned_empty((5, 3, 64, 64))
+    zo = model.pinned_empty((5, 100))
+    t = model.reconstruct_submit(batches[0], out, zo)
+    model.reconstruct_wait(t)
+    assert np.abs(out - want[0]).max() <= 2e-5 and np.abs(zo - model.encode_images(batches[0])).max() <= 2e-5
+    with pytest.raises(TypeError):
+        model.reconstruct(batches[0], out=np.empty((4, 3, 64, 64), np.float32))
+
+
 def test_loader_rejects_bad_checkpoints(npe, weights):
     bad = dict(weights)
     bad["enc_conv2.W"] = bad["enc_conv2.W"][:, :64]
