@@ -113,3 +113,88 @@ def edit_loop(P, z, boxes, rgb, n_steps=32, weight=0.05):
         g = grad_batched(P, z, boxes, rgb)
         z = z - weight * g * fac
     return z
+
+
+# ================================================================================================
+# FULL IAN graph (reference IAN.py:67-228; layers.py:207-258, 397-416, 641-853), float32/64 functional
+# ================================================================================================
+
+def mdcl(P, name, x, scales):
+    """MDCL (layers.py:207-258) through F.conv2d (independent of the tap-loop form in ian_full_numpy)."""
+    W = P[name + "W"]
+    y = F.conv2d(x, W * P[name + "_coeff_base"].reshape(-1, 1, 1, 1), padding=1)
+    for s in scales:
+        if s == 0:
+            y = y + F.conv2d(x, (W.mean(dim=(2, 3)) * P[name + "_coeff_1x1"].reshape(-1, 1))[:, :, None, None])
+        else:
+            y = y + F.conv2d(x, W * P[name + "_coeff_%d" % s].reshape(-1, 1, 1, 1), padding=s, dilation=s)
+    return y
+
+
+def mdcl_composite(P, name, x, scales):
+    """mdclW formulation (layers.py:138-150 idea): ONE conv with the composite (2*smax+1)^2 kernel.
+    KAT: must equal mdcl()."""
+    W = P[name + "W"]
+    smax = max([1] + [s for s in scales])
+    K = 2 * smax + 1
+    comp = torch.zeros(W.shape[0], W.shape[1], K, K, dtype=W.dtype)
+
+    def put(s, coeff):
+        for i in range(3):
+            for j in range(3):
+                comp[:, :, smax + (i - 1) * s, smax + (j - 1) * s] += W[:, :, i, j] * coeff.reshape(-1, 1)
+    put(1, P[name + "_coeff_base"])
+    for s in scales:
+        if s == 0:
+            comp[:, :, smax, smax] += W.mean(dim=(2, 3)) * P[name + "_coeff_1x1"].reshape(-1, 1)
+        else:
+            put(s, P[name + "_coeff_%d" % s])
+    return F.conv2d(x, comp, padding=smax)
+
+
+def mdblock(P, name, x, scales, mdcl_fn=mdcl):
+    t = _lrelu(_bn(P, name + "bnorm0", x))
+    t = _lrelu(_bn(P, name + "bnorm1", mdcl_fn(P, name, t, scales)))
+    t = mdcl_fn(P, name + "2", t, scales)
+    return _lrelu(_bn(P, name + "bnorm2", x + t))
+
+
+def made(P, name, z, masks):
+    M0, M1, Md = masks
+    h = _relu(z @ (P[name + "_input.W"] * M0) + P[name + "_input.b"])
+    return h @ (P[name + "_output_W.W"] * M1) + P[name + "_output_W.b"] + z @ (P[name + "_output_D.W"] * Md) + P[name + "_output_D.b"]
+
+
+def full_encode_mu_ls(P, x):
+    h = _lrelu(F.conv2d(x, P["enc_conv1.W"], P["enc_conv1.b"], stride=2, padding=2))
+    h = _lrelu(_bn(P, "bnorm2", F.conv2d(h, P["enc_conv2.W"], None, stride=2, padding=2)))
+    h = _lrelu(_bn(P, "bnorm3", F.conv2d(h, P["enc_conv3.W"], None, stride=2, padding=2)))
+    h = _lrelu(_bn(P, "bnorm4", F.conv2d(h, P["enc_conv4.W"], None, stride=2, padding=2)))
+    h = _relu(_bn(P, "bnorm_enc_fc1", h.flatten(1) @ P["enc_fc1.W"]))
+    return _bn(P, "mu_bnorm", h @ P["enc_mu.W"]), _bn(P, "ls_bnorm", h @ P["enc_logsigma.W"])
+
+
+def full_latent(P, z_iaf, masks):
+    return (z_iaf - made(P, "l_IAF_mu", z_iaf, masks)) / torch.exp(made(P, "l_IAF_ls", z_iaf, masks))
+
+
+def full_encode(P, x, masks, deterministic=True, eps=None):
+    mu, ls = full_encode_mu_ls(P, x)
+    z = mu if deterministic else mu + torch.exp(ls) * eps
+    return full_latent(P, z, masks)
+
+
+def full_decode(P, z, mdcl_fn=mdcl):
+    h = _lrelu(z @ P["l_dec_fc2.W"] + P["l_dec_fc2.b"]).reshape(-1, 512, 4, 4)
+    h = mdblock(P, "dec_conv2a", deconv(h, P["dec_conv1.W"]), [0, 2], mdcl_fn)
+    h = mdblock(P, "dec_conv3a", deconv(h, P["dec_conv2.W"]), [0, 2, 3], mdcl_fn)
+    h = mdblock(P, "dec_conv4a", deconv(h, P["dec_conv3.W"]), [0, 2, 3], mdcl_fn)
+    h = _lrelu(_bn(P, "bnorm_dc4", deconv(h, P["dec_conv4.W"])))
+    sc = [2, 3, 4]
+    R = torch.sigmoid(mdcl_fn(P, "R", h, sc))
+    G = torch.sigmoid(mdcl_fn(P, "G_a", h, sc) + mdcl_fn(P, "G_b", R, sc))
+    B = torch.sigmoid(mdcl_fn(P, "B_a", h, sc) + mdcl_fn(P, "B_b", torch.cat([R, G], 1), sc))
+
+    def beta(a, b):
+        return 2.0 * (a / (a + b + 1e-8)) - 1.0
+    return torch.stack([beta(R[:, 0], R[:, 1]), beta(G[:, 0], G[:, 1]), beta(B[:, 0], B[:, 1])], 1)

@@ -52,3 +52,56 @@ def save_checkpoint(fname, P, metadata=None):
     d["metadata"] = np.frombuffer(pickle.dumps(metadata or {"epoch": 0, "itr": 0}, protocol=2),
                                   dtype=np.uint8)
     np.savez_compressed(fname, **d)
+
+
+# ---- full IAN (reference IAN.py:67-228) -------------------------------------------------------------
+def _mdcl_shapes(name, F, C, scales):
+    out = [(name + "W", (F, C, 3, 3)), (name + "_coeff_base", ("coeff", F))]
+    for s in scales:
+        out.append((name + ("_coeff_1x1" if s == 0 else "_coeff_%d" % s), ("coeff", F)))
+    return out
+
+
+def _mdblock_shapes(name, F, scales):
+    return (_mdcl_shapes(name, F, F, scales) + _mdcl_shapes(name + "2", F, F, scales) +
+            [(name + "bnorm0", F), (name + "bnorm1", F), (name + "bnorm2", F)])
+
+
+def full_shapes():
+    enc = [s for s in SIMPLE_SHAPES if s[0].startswith(("enc_", "bnorm2", "bnorm3", "bnorm4", "bnorm_enc", "mu_", "ls_"))]
+    made = []
+    for name in ("l_IAF_mu", "l_IAF_ls"):
+        for sub in ("_input", "_output_W", "_output_D"):
+            made += [(name + sub + ".W", ("made", (100, 100))), (name + sub + ".b", ("made", (100,)))]
+    dec = [("l_dec_fc2.W", (100, 8192)), ("l_dec_fc2.b", (8192,)), ("dec_conv1.W", (512, 512, 5, 5))]
+    dec += _mdblock_shapes("dec_conv2a", 512, [0, 2]) + [("dec_conv2.W", (512, 256, 5, 5))]
+    dec += _mdblock_shapes("dec_conv3a", 256, [0, 2, 3]) + [("dec_conv3.W", (256, 128, 5, 5))]
+    dec += _mdblock_shapes("dec_conv4a", 128, [0, 2, 3]) + [("dec_conv4.W", (128, 128, 5, 5)), ("bnorm_dc4", 128)]
+    sc = [2, 3, 4]
+    dec += (_mdcl_shapes("R", 2, 128, sc) + _mdcl_shapes("G_a", 2, 128, sc) + _mdcl_shapes("G_b", 2, 2, sc) +
+            _mdcl_shapes("B_a", 2, 128, sc) + _mdcl_shapes("B_b", 2, 4, sc))
+    return enc + made + dec
+
+
+def make_full_weights(seed=0, w_std=0.02):
+    """Synthetic weights for the IAN.py graph.  MDCL coefficients ~U(0.1,0.5) (reference init is the constant
+    1/(1+len(scales)), layers.py:214: randomised so that a swapped coefficient shows); MADE W,b ~N(0,0.1)."""
+    rng = np.random.default_rng(seed)
+    P = {}
+    for name, shp in full_shapes():
+        if isinstance(shp, int):
+            P[name + ".gamma"] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+            P[name + ".beta"] = rng.normal(0, 0.1, shp).astype(np.float32)
+            P[name + ".mean"] = rng.normal(0, 0.1, shp).astype(np.float32)
+            P[name + ".inv_std"] = rng.uniform(0.5, 2.0, shp).astype(np.float32)
+        elif shp[0] == "coeff":
+            P[name] = rng.uniform(0.1, 0.5, shp[1]).astype(np.float32)
+        elif shp[0] == "made":
+            P[name] = rng.normal(0, 0.1, shp[1]).astype(np.float32)
+        elif name in ("enc_conv1.b", "l_dec_fc2.b"):
+            P[name] = rng.normal(0, 0.02, shp).astype(np.float32)
+        else:
+            # 3x3 MDC filters get a larger std so that the residual branch is not negligible next to x
+            std = 0.05 if (name.endswith("W") and not name.endswith(".W")) else w_std
+            P[name] = rng.normal(0, std, shp).astype(np.float32)
+    return P
