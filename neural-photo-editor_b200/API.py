@@ -29,6 +29,25 @@ _SIMPLE_CFG = {
     'recon_weight': 3.0, 'feature_weight': 1.0,
 }
 _SIMPLE_MODEL_KEYS = ('l_in', 'l_out', 'l_mu', 'l_ls', 'l_Z', 'l_introspect', 'l_discrim')
+# cfg of reference IAN.py:39-62
+_FULL_CFG = {
+    'batch_size': 16, 'learning_rate': {0: 0.0002, 25: 0.0001, 50: 0.00005, 75: 0.00001}, 'optimizer': 'Adam',
+    'beta1': 0.5, 'update_ratio': 1, 'decay_rate': 0, 'reg': 1e-5, 'momentum': 0.9, 'shuffle': True, 'dims': (64, 64),
+    'n_channels': 3, 'batches_per_chunk': 64, 'max_epochs': 80, 'checkpoint_every_nth': 1, 'num_latents': 100,
+    'recon_weight': 3.0, 'feature_weight': 1.0, 'dg_weight': 1.0, 'dd_weight': 1.0, 'agr_weight': 1.0,
+    'ags_weight': 1.0, 'n_shuffles': 1, 'ortho': 1e-3,
+}
+_FULL_MODEL_KEYS = _SIMPLE_MODEL_KEYS + ('l_IAF_mu', 'l_IAF_ls', 'l_Z_IAF')
+
+
+def made_ordering(seed=1234, n=100):
+    """MADE input ordering after `reset("Once")` (reference API.py:33-36 -> layers.py:845-853 ->
+    mask_generator.py:35-38,55-73): one shuffle_row_elements draw of theano RandomStreams(seed).  Recalled theano
+    seeding (unverifiable offline): the stream's generator is
+    RandomState(RandomState(seed).randint(2**30)) and a 1-D shuffle is one permutation(n).  Pass
+    `made_ordering=` to IAN(...) to override."""
+    stream = np.random.RandomState(int(np.random.RandomState(seed).randint(2 ** 30)))
+    return np.arange(n, dtype=np.int32)[stream.permutation(n)]
 
 
 def _f32(a, ndim, what):
@@ -57,21 +76,26 @@ def _fp(a):
 class IAN:
     """Generic class for using IAN style models with the NPE (reference API.py:11)."""
 
-    def __init__(self, config_path, dnn=True, weights=None, device=0, path=None):
+    def __init__(self, config_path, dnn=True, weights=None, device=0, path=None, made_ordering=None):
         """config_path: path of the reference-style config module ('IAN_simple.py'); the weights are read
         from config_path[:-3]+'.npz' in GANcheckpoints format (reference API.py:18-30) unless a
         {name: ndarray} dict is given in `weights`.  `dnn` is accepted for signature compatibility (both
         reference variants of the graph are numerically the same function, IAN_simple.py:141-223)."""
         base = os.path.basename(str(config_path))
-        if base != 'IAN_simple.py':
-            raise NotImplementedError("config %r: only the IAN_simple graph is built so far" % base)
-        self.cfg = dict(_SIMPLE_CFG)
+        if base == 'IAN_simple.py':
+            kind, self.cfg, keys = _lib.IAN_MODEL_SIMPLE, dict(_SIMPLE_CFG), _SIMPLE_MODEL_KEYS
+        elif base == 'IAN.py':
+            # the reference's own API.IAN cannot construct this config (get_model(interp=...) vs dnn=..., SURVEY F6)
+            kind, self.cfg, keys = _lib.IAN_MODEL_FULL, dict(_FULL_CFG), _FULL_MODEL_KEYS
+        else:
+            raise NotImplementedError("config %r: the IAN_simple.py and IAN.py graphs are built; IANv1.py is not" % base)
+        self.kind = kind
         self.weights_fname = str(config_path)[:-3] + '.npz'
-        self.model = {k: 'IAN_simple.' + k for k in _SIMPLE_MODEL_KEYS}
+        self.model = {k: base[:-3] + '.' + k for k in keys}
         self.dnn = dnn
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        rc = self._lib.ian_create(_lib.IAN_MODEL_SIMPLE, int(device), C.byref(self._h))
+        rc = self._lib.ian_create(kind, int(device), C.byref(self._h))
         if rc != _lib.IAN_OK:
             msg = self._lib.ian_last_error(None)
             self._h = None
@@ -87,6 +111,11 @@ class IAN:
                 continue   # discriminator head: not on the hot path (IAN_simple.py:225-231)
             shape = (C.c_int64 * arr.ndim)(*arr.shape)
             self._check(self._lib.ian_set_param(self._h, name.encode(), _fp(arr), shape, arr.ndim))
+        if kind == _lib.IAN_MODEL_FULL:
+            print('Shuffling MADE masks')                   # reference API.py:33-36
+            o = np.ascontiguousarray(globals()['made_ordering']() if made_ordering is None else made_ordering, np.int32)
+            self.made_ordering = o
+            self._check(self._lib.ian_set_made_ordering(self._h, o.ctypes.data_as(C.POINTER(C.c_int32)), int(o.size)))
         self._check(self._lib.ian_finalize(self._h))
         if path is not None:
             self.set_path(path)

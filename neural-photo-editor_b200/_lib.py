@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libian_b200.so")
 
 IAN_OK = 0
 IAN_PATH_TC, IAN_PATH_SIMT = 0, 1
-IAN_MODEL_SIMPLE = 0
+IAN_MODEL_SIMPLE, IAN_MODEL_FULL = 0, 1
 
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int32)
@@ -20,6 +20,7 @@ _H = C.c_void_p
 SIGNATURES = {
     "ian_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_H)]),
     "ian_set_param": (C.c_int, [_H, C.c_char_p, _F, C.POINTER(C.c_int64), C.c_int]),
+    "ian_set_made_ordering": (C.c_int, [_H, _I, C.c_int]),
     "ian_finalize": (C.c_int, [_H]),
     "ian_destroy": (C.c_int, [_H]),
     "ian_last_error": (C.c_char_p, [_H]),

@@ -15,6 +15,11 @@ int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* 
                           long long plane, int n, cudaStream_t st);
 int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
                         __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st);
+// full IAN: MADE+IAF latent flow and the autoregressive RGB-Beta head
+int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
+                    cudaStream_t st);
+int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
+                         float* xhat, int n, cudaStream_t st);
 // dec_out on the tensor-core path (decout_tc.cu)
 struct DecOutMaps;
 DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,

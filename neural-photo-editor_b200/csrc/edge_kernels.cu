@@ -280,6 +280,116 @@ __global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// full IAN latent: z = (z0 - MADE_mu(z0)) / exp(MADE_ls(z0))     (reference IAN.py:126-128; layers.py:641-853)
+//   MADE(z) = relu(z (W0*M0) + b0) (W1*M1) + b1 + z (Wd*Md) + bd ; the masks are pre-multiplied on the host
+// mw: [2 nets][3 matrices: input, output_W, output_D][100][100] fp32 (in,out); mb: [2][3][100].
+// one block per sample, 128 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) made_iaf_kernel(const float* __restrict__ z0, const float* __restrict__ mw,
+                                                       const float* __restrict__ mb, float* __restrict__ z,
+                                                       __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  __shared__ float zs[100];
+  __shared__ float hs[2][100];
+  const int k = blockIdx.x, j = threadIdx.x;
+  if (j < 100) zs[j] = z0[k * 100 + j];
+  __syncthreads();
+  if (j < 100) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      const float* W0 = mw + (net * 3 + 0) * 10000;
+      float a = mb[(net * 3 + 0) * 100 + j];
+      for (int i = 0; i < 100; ++i) a = fmaf(zs[i], W0[i * 100 + j], a);
+      hs[net][j] = 0.5f * (a + fabsf(a));
+    }
+  }
+  __syncthreads();
+  float out = 0.f;
+  if (j < 100) {
+    float o[2];
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      const float* W1 = mw + (net * 3 + 1) * 10000;
+      const float* Wd = mw + (net * 3 + 2) * 10000;
+      float a = mb[(net * 3 + 1) * 100 + j] + mb[(net * 3 + 2) * 100 + j];
+      float a1 = 0.f, a2 = 0.f;
+      for (int i = 0; i < 100; ++i) {
+        a1 = fmaf(hs[net][i], W1[i * 100 + j], a1);
+        a2 = fmaf(zs[i], Wd[i * 100 + j], a2);
+      }
+      o[net] = a + a1 + a2;
+    }
+    out = (zs[j] - o[0]) / expf(o[1]);                   // IAFLayer (layers.py:649)
+    if (z) z[k * 100 + j] = out;
+  }
+  if (zp) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(j < 100 ? out : 0.f, hi, lo);
+    zp[k * 128 + j] = hi;
+    zp[zplane + k * 128 + j] = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// full IAN RGB-Beta head (reference IAN.py:183-207; layers.py:397-408).  ha (n,64,64,16) fp32 holds the three
+// 128->2 MDC convolutions of the feature map: [R | G_a | B_a | pad].  The autoregressive parts are 2->2 and
+// 4->2 channel MDC convolutions over 33 dilated taps: a few hundred MACs per pixel, done per pixel here.
+//   R = sig(ha[0:2]);  G = sig(ha[2:4] + MDC_Gb(R));  B = sig(ha[4:6] + MDC_Bb([R,G]));
+//   out_c = 2 a/(a+b+1e-8) - 1
+// taps: [33][2] int (dy,dx);  wgb: [33][2 out][2 in];  wbb: [33][2 out][4 in]   (composite MDC weights)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void head_r_kernel(const float* __restrict__ ha, float* __restrict__ rg, long long npix) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float2 a = *reinterpret_cast<const float2*>(ha + i * 16);
+  float4 o = make_float4(sigmoidf_(a.x), sigmoidf_(a.y), 0.f, 0.f);
+  *reinterpret_cast<float4*>(rg + i * 4) = o;            // rg: (n,64,64,4) = [R0,R1,G0,G1]
+}
+
+__global__ void head_g_kernel(const float* __restrict__ ha, float* __restrict__ rg, const int* __restrict__ taps,
+                              const float* __restrict__ wgb, int ntaps, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * 4096) return;
+  const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
+  const long long img = i >> 12;
+  float g0 = ha[i * 16 + 2], g1 = ha[i * 16 + 3];
+  for (int t = 0; t < ntaps; ++t) {
+    const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
+    if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
+    const float2 r = *reinterpret_cast<const float2*>(rg + ((img * 64 + pp) * 64 + qq) * 4);
+    const float4 w = *reinterpret_cast<const float4*>(wgb + t * 4);     // [out0: in0,in1 | out1: in0,in1]
+    g0 = fmaf(r.x, w.x, fmaf(r.y, w.y, g0));
+    g1 = fmaf(r.x, w.z, fmaf(r.y, w.w, g1));
+  }
+  *reinterpret_cast<float2*>(rg + i * 4 + 2) = make_float2(sigmoidf_(g0), sigmoidf_(g1));
+}
+
+__global__ void head_b_out_kernel(const float* __restrict__ ha, const float* __restrict__ rg, const int* __restrict__ taps,
+                                  const float* __restrict__ wbb, int ntaps, float* __restrict__ xhat, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * 4096) return;
+  const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
+  const long long img = i >> 12;
+  float b0 = ha[i * 16 + 4], b1 = ha[i * 16 + 5];
+  for (int t = 0; t < ntaps; ++t) {
+    const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
+    if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
+    const float4 v = *reinterpret_cast<const float4*>(rg + ((img * 64 + pp) * 64 + qq) * 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(wbb + t * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(wbb + t * 8 + 4);
+    b0 = fmaf(v.x, w0.x, fmaf(v.y, w0.y, fmaf(v.z, w0.z, fmaf(v.w, w0.w, b0))));
+    b1 = fmaf(v.x, w1.x, fmaf(v.y, w1.y, fmaf(v.z, w1.z, fmaf(v.w, w1.w, b1))));
+  }
+  const float4 me = *reinterpret_cast<const float4*>(rg + i * 4);
+  const float B0 = sigmoidf_(b0), B1 = sigmoidf_(b1);
+  float* o = xhat + img * 3 * 4096 + p * 64 + q;
+  o[0] = 2.f * (me.x / (me.x + me.y + 1e-8f)) - 1.f;     // beta_layer (layers.py:408)
+  o[4096] = 2.f * (me.z / (me.z + me.w + 1e-8f)) - 1.f;
+  o[8192] = 2.f * (B0 / (B0 + B1 + 1e-8f)) - 1.f;
+}
+
 }  // namespace
 
 #define CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 1 : -1)
@@ -328,4 +438,22 @@ int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, f
   return CHECK_LAUNCH();
 }
 
+}  // namespace ian
+
+namespace ian {
+int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
+                    cudaStream_t st) {
+  made_iaf_kernel<<<n, 128, 0, st>>>(z0, mw, mb, z, zp, zplane, n);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
+                         float* xhat, int n, cudaStream_t st) {
+  const long long npix = (long long)n * 4096;
+  const unsigned blocks = (unsigned)((npix + 255) / 256);
+  head_r_kernel<<<blocks, 256, 0, st>>>(ha, rg, npix);
+  head_g_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wgb, ntaps, n);
+  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wbb, ntaps, xhat, n);
+  return cudaGetLastError() == cudaSuccess ? 3 : -1;
+}
 }  // namespace ian

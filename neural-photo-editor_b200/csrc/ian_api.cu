@@ -66,13 +66,69 @@ const BnSpec kSimpleBn[] = {{"bnorm2", 256},       {"bnorm3", 512},     {"bnorm4
                             {"bnorm_dc1", 512},    {"bnorm_dc2", 256},  {"bnorm_dc3", 128}};
 const char* kBnFields[] = {"beta", "gamma", "mean", "inv_std"};
 
+struct Spec { std::string name; std::vector<int64_t> shape; };
+
+void add_bn(std::vector<Spec>& v, const std::string& name, int64_t c) {
+  for (const char* f : kBnFields) v.push_back({name + "." + f, {c}});
+}
+void add_mdcl(std::vector<Spec>& v, const std::string& name, int64_t F, int64_t C, std::initializer_list<int> scales) {
+  v.push_back({name + "W", {F, C, 3, 3}});
+  v.push_back({name + "_coeff_base", {F}});
+  for (int s : scales) v.push_back({name + (s == 0 ? std::string("_coeff_1x1") : "_coeff_" + std::to_string(s)), {F}});
+}
+void add_mdblock(std::vector<Spec>& v, const std::string& name, int64_t F, std::initializer_list<int> scales) {
+  add_mdcl(v, name, F, F, scales);
+  add_mdcl(v, name + "2", F, F, scales);
+  add_bn(v, name + "bnorm0", F); add_bn(v, name + "bnorm1", F); add_bn(v, name + "bnorm2", F);
+}
+
+// parameter names / shapes of a model kind, in the reference's checkpoint naming (GANcheckpoints.py:11-30)
+std::vector<Spec> spec_list(int kind) {
+  std::vector<Spec> v;
+  if (kind == IAN_MODEL_SIMPLE) {
+    for (const auto& s : kSimpleWeights) v.push_back({s.name, std::vector<int64_t>(s.shape, s.shape + s.ndim)});
+    for (const auto& b : kSimpleBn) add_bn(v, b.name, b.c);
+    return v;
+  }
+  // IAN.py:67-207
+  for (const auto& s : kSimpleWeights) {
+    const std::string n = s.name;
+    if (n.rfind("enc_", 0) == 0) v.push_back({n, std::vector<int64_t>(s.shape, s.shape + s.ndim)});
+  }
+  for (const char* b : {"bnorm2", "bnorm3", "bnorm4"}) add_bn(v, b, b[5] == '2' ? 256 : b[5] == '3' ? 512 : 1024);
+  add_bn(v, "bnorm_enc_fc1", 1000); add_bn(v, "mu_bnorm", 100); add_bn(v, "ls_bnorm", 100);
+  for (const char* m : {"l_IAF_mu", "l_IAF_ls"})
+    for (const char* sub : {"_input", "_output_W", "_output_D"}) {
+      v.push_back({std::string(m) + sub + ".W", {100, 100}});
+      v.push_back({std::string(m) + sub + ".b", {100}});
+    }
+  v.push_back({"l_dec_fc2.W", {100, 8192}}); v.push_back({"l_dec_fc2.b", {8192}});
+  v.push_back({"dec_conv1.W", {512, 512, 5, 5}});
+  add_mdblock(v, "dec_conv2a", 512, {0, 2});
+  v.push_back({"dec_conv2.W", {512, 256, 5, 5}});
+  add_mdblock(v, "dec_conv3a", 256, {0, 2, 3});
+  v.push_back({"dec_conv3.W", {256, 128, 5, 5}});
+  add_mdblock(v, "dec_conv4a", 128, {0, 2, 3});
+  v.push_back({"dec_conv4.W", {128, 128, 5, 5}});
+  add_bn(v, "bnorm_dc4", 128);
+  add_mdcl(v, "R", 2, 128, {2, 3, 4}); add_mdcl(v, "G_a", 2, 128, {2, 3, 4}); add_mdcl(v, "G_b", 2, 2, {2, 3, 4});
+  add_mdcl(v, "B_a", 2, 128, {2, 3, 4}); add_mdcl(v, "B_b", 2, 4, {2, 3, 4});
+  return v;
+}
+
 enum LayerId {
   L_ENC_CONV2 = 0, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3,
-  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2, L_COUNT,
+  L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2,
+  // full IAN decoder (reference IAN.py:129-207)
+  F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD,
+  L_COUNT,
   T_CONV1 = L_COUNT, T_DEC_OUT, T_COUNT   // timing-only slots of the two edge kernels
 };
 const char* kLayerNames[T_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "l_dec_fc2", "dec_conv1",
-                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2", "enc_conv1", "dec_out"};
+                                    "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2",
+                                    "full_dec_fc2", "full_dec_conv1", "dec_conv2a", "dec_conv2a2", "full_dec_conv2", "dec_conv3a", "dec_conv3a2",
+                                    "full_dec_conv3", "dec_conv4a", "dec_conv4a2", "full_dec_conv4", "rgb_head",
+                                    "enc_conv1", "dec_out"};
 
 struct DevWeights {           // one GEMM layer's B operand + epilogue vectors
   __nv_bfloat16* b = nullptr;
@@ -103,9 +159,14 @@ struct ian_handle {
   float* conv1_b = nullptr;    // [128]
   float* decout_wt = nullptr;  // [25][128][4] fp32 (SIMT forward + brush backward)
   __nv_bfloat16* decout_tc_wt = nullptr;   // [2][80][128] bf16 planes, row = tap*3+co (tensor-core forward)
+  // full IAN extras
+  std::vector<int32_t> made_ordering;       // MADE input ordering (mask_generator.py:35-38); set by ian_set_made_ordering
+  float *made_w = nullptr, *made_b = nullptr;   // [2][3][100][100] masked weights (in,out), [2][3][100] biases
+  int* head_taps = nullptr;                 // [33][2] (dy,dx) of the scales-[2,3,4] MDC
+  float *head_wgb = nullptr, *head_wbb = nullptr;   // composite G_b [33][2][2], B_b [33][2][4]
+  int head_ntaps = 0;
   std::map<int, Plan*> plans;
   int max_chunk = 512;
-  int tc_merged = 0;           // IAN_TC_MERGED=1: single TMEM accumulator per tile (enables double buffering at BN=256)
   bool timing = false;
   struct Timed { cudaEvent_t e0, e1; };
   std::vector<Timed> timed[T_COUNT];
@@ -149,6 +210,9 @@ struct Plan {
   float *x = nullptr, *head = nullptr, *z = nullptr, *xhat = nullptr, *gpad = nullptr, *ws_fc1 = nullptr, *eps = nullptr;
   float* target = nullptr;
   int32_t* boxes = nullptr;
+  // full IAN activations (NHWC split planes): block input x, pre-activated t0, mid t2, block output y per scale
+  Planes fh0, fx1, ft1, fu1, fy1, fx2, ft2, fu2, fy2, fx3, ft3, fu3, fy3, fh4;
+  float *z0 = nullptr, *ha = nullptr, *rg = nullptr;
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
   DecOutMaps* decout_maps = nullptr;
@@ -229,6 +293,27 @@ void taps_dense(TapGemm& g) {
   g.osh = g.osw = 1;
 }
 
+// distinct tap offsets of an MDC layer (reference layers.py:207-258): 3x3 base, then 3x3 dilated by each s > 0
+// (0 in scales = the 1x1 mean filter, which lands on the centre tap).  17 / 25 / 33 offsets for [0,2] / [0,2,3] / [2,3,4].
+std::vector<std::pair<int, int>> mdc_offsets(const std::vector<int>& scales) {
+  std::vector<std::pair<int, int>> off;
+  auto add = [&](int dy, int dx) {
+    for (auto& o : off) if (o.first == dy && o.second == dx) return;
+    off.push_back({dy, dx});
+  };
+  for (int i = -1; i <= 1; ++i) for (int j = -1; j <= 1; ++j) add(i, j);
+  for (int s : scales) if (s > 0) for (int i = -1; i <= 1; ++i) for (int j = -1; j <= 1; ++j) add(i * s, j * s);
+  return off;
+}
+void taps_mdc(TapGemm& g, const std::vector<int>& scales) {
+  const auto off = mdc_offsets(scales);
+  g.nphase = 1;
+  g.phase[0] = {0, (int)off.size(), 0, 0};
+  for (size_t t = 0; t < off.size(); ++t) g.taps[t] = {0, (int16_t)off[t].first, (int16_t)off[t].second, (int16_t)t};
+  g.sh = g.sw = 1;
+  g.osh = g.osw = 1;
+}
+
 void set_io(TapGemm& g, const Planes& a, int n, int Hin, int Win, int Cin, int Hg, int Wg, const DevWeights& w,
             int Hout, int Wout) {
   g.a = a.p; g.a_plane = a.plane;
@@ -237,6 +322,7 @@ void set_io(TapGemm& g, const Planes& a, int n, int Hin, int Win, int Cin, int H
   g.scale = w.scale; g.shift = w.shift; g.scale_pix_stride = 0;
   g.Hout = Hout; g.Wout = Wout;
   g.ksplit = 1; g.ws = nullptr; g.mask = nullptr; g.out = nullptr; g.out_f32 = nullptr; g.out_plane = 0;
+  g.res = nullptr; g.res_plane = 0; g.out_raw = nullptr; g.out_raw_plane = 0;
 }
 
 int choose_ksplit(const TapGemm& g) {
@@ -256,20 +342,78 @@ int choose_ksplit(const TapGemm& g) {
   return ks;
 }
 
+int finish_maps(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
+  for (int l : layers) {
+    char err[256] = {0};
+    pl->maps[l] = tc_build_maps(pl->g[l], err, sizeof(err));
+    if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
+    if (pl->g[l].ws) {
+      pl->g[l].ksplit = choose_ksplit(pl->g[l]);
+      if (pl->g[l].ksplit == 1) pl->g[l].ws = nullptr;
+    }
+  }
+  return IAN_OK;
+}
+
+// decoder of the full IAN (reference IAN.py:129-207): dense -> 3 x (deconv, MDBLOCK) -> deconv -> RGB-Beta head
+int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
+  TapGemm* g = pl->g;
+  const int n = pl->n;
+  auto outp = [](TapGemm& gg, const Planes& t) { gg.out = t.p; gg.out_plane = t.plane; };
+  set_io(g[F_DEC_FC2], pl->zp, n, 1, 1, 128, 1, 1, h->w[F_DEC_FC2], 1, 1); taps_dense(g[F_DEC_FC2]);
+  g[F_DEC_FC2].act = ACT_LRELU; outp(g[F_DEC_FC2], pl->fh0);
+  struct Stage { int dconv, mda, mdb; const Planes *in, *x, *t, *u, *y; int Hin, Cin, Cout; std::vector<int> scales; };
+  const Stage st[3] = {{F_DEC_CONV1, F_MD1A, F_MD1B, &pl->fh0, &pl->fx1, &pl->ft1, &pl->fu1, &pl->fy1, 4, 512, 512, {0, 2}},
+                       {F_DEC_CONV2, F_MD2A, F_MD2B, &pl->fy1, &pl->fx2, &pl->ft2, &pl->fu2, &pl->fy2, 8, 512, 256, {0, 2, 3}},
+                       {F_DEC_CONV3, F_MD3A, F_MD3B, &pl->fy2, &pl->fx3, &pl->ft3, &pl->fu3, &pl->fy3, 16, 256, 128, {0, 2, 3}}};
+  for (const Stage& s : st) {
+    const int Ho = 2 * s.Hin;
+    // deconv: raw sum -> x (block residual), lrelu(BN0(x)) -> t    (layers.py:413: BN(incoming) strips the bias)
+    set_io(g[s.dconv], *s.in, n, s.Hin, s.Hin, s.Cin, s.Hin, s.Hin, h->w[s.dconv], Ho, Ho); taps_deconv_s2(g[s.dconv]);
+    g[s.dconv].act = ACT_LRELU; outp(g[s.dconv], *s.t);
+    g[s.dconv].out_raw = s.x->p; g[s.dconv].out_raw_plane = s.x->plane;
+    // MDCL 1: lrelu(BN1(.)) ; MDCL 2: lrelu(BN2(x + .))
+    set_io(g[s.mda], *s.t, n, Ho, Ho, s.Cout, Ho, Ho, h->w[s.mda], Ho, Ho); taps_mdc(g[s.mda], s.scales);
+    g[s.mda].act = ACT_LRELU; outp(g[s.mda], *s.u);
+    set_io(g[s.mdb], *s.u, n, Ho, Ho, s.Cout, Ho, Ho, h->w[s.mdb], Ho, Ho); taps_mdc(g[s.mdb], s.scales);
+    g[s.mdb].act = ACT_LRELU; outp(g[s.mdb], *s.y);
+    g[s.mdb].res = s.x->p; g[s.mdb].res_plane = s.x->plane;
+  }
+  set_io(g[F_DEC_CONV4], pl->fy3, n, 32, 32, 128, 32, 32, h->w[F_DEC_CONV4], 64, 64); taps_deconv_s2(g[F_DEC_CONV4]);
+  g[F_DEC_CONV4].act = ACT_LRELU; outp(g[F_DEC_CONV4], pl->fh4);
+  set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_mdc(g[F_HEAD], {2, 3, 4});
+  g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32 = pl->ha;
+  int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
+                               F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD});
+  if (rc != IAN_OK) return rc;
+  *out = pl;
+  return IAN_OK;
+}
+
 int build_plan(ian_handle* h, int n, Plan** out) {
   Plan* pl = new Plan();
   pl->n = n;
   const long long N = n;
   int rc;
 #define AP(t, e) if ((rc = alloc_planes(h, pl, pl->t, (e))) != IAN_OK) return rc;
+#define AB(t, e) if ((rc = alloc_buf(h, pl, pl->t, (e))) != IAN_OK) return rc;
+  const bool full = h->model_kind == IAN_MODEL_FULL;
   AP(a1, N * 32 * 32 * 128) AP(a2, N * 16 * 16 * 256) AP(a3, N * 8 * 8 * 512) AP(a4, N * 4 * 4 * 1024)
   AP(f1, N * 1024) AP(zp, N * 128)
-  AP(h0, N * 16384) AP(h1, N * 8 * 8 * 512) AP(h2, N * 16 * 16 * 256) AP(h3, N * 32 * 32 * 128)
-  AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
+  AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(ws_fc1, N * 1024) AB(eps, N * 100)
+  if (!full) {
+    AP(h0, N * 16384) AP(h1, N * 8 * 8 * 512) AP(h2, N * 16 * 16 * 256) AP(h3, N * 32 * 32 * 128)
+    AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
+    AB(gpad, N * 128) AB(target, N * 3 * 4096) AB(boxes, N * 4)
+  } else {
+    AP(fh0, N * 8192)
+    AP(fx1, N * 64 * 512) AP(ft1, N * 64 * 512) AP(fu1, N * 64 * 512) AP(fy1, N * 64 * 512)
+    AP(fx2, N * 256 * 256) AP(ft2, N * 256 * 256) AP(fu2, N * 256 * 256) AP(fy2, N * 256 * 256)
+    AP(fx3, N * 1024 * 128) AP(ft3, N * 1024 * 128) AP(fu3, N * 1024 * 128) AP(fy3, N * 1024 * 128)
+    AP(fh4, N * 4096 * 128)
+    AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4)
+  }
 #undef AP
-#define AB(t, e) if ((rc = alloc_buf(h, pl, pl->t, (e))) != IAN_OK) return rc;
-  AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(gpad, N * 128)
-  AB(ws_fc1, N * 1024) AB(eps, N * 100) AB(target, N * 3 * 4096) AB(boxes, N * 4)
 #undef AB
 
   TapGemm* g = pl->g;
@@ -282,9 +426,11 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_ENC_CONV4], pl->a3, n, 8, 8, 512, 4, 4, h->w[L_ENC_CONV4], 4, 4); taps_conv_s2(g[L_ENC_CONV4]);
   g[L_ENC_CONV4].act = ACT_LRELU; g[L_ENC_CONV4].out = pl->a4.p; g[L_ENC_CONV4].out_plane = pl->a4.plane;
   set_io(g[L_ENC_FC1], pl->a4, n, 1, 1, 16384, 1, 1, h->w[L_ENC_FC1], 1, 1); taps_dense(g[L_ENC_FC1]);
-  g[L_ENC_FC1].act = ACT_ELU; g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ws = pl->ws_fc1;
+  g[L_ENC_FC1].act = full ? ACT_RELU : ACT_ELU;   // IAN.py:118 uses rectify, IAN_simple.py:121 elu
+  g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ws = pl->ws_fc1;
   set_io(g[L_ENC_HEAD], pl->f1, n, 1, 1, 1024, 1, 1, h->w[L_ENC_HEAD], 1, 1); taps_dense(g[L_ENC_HEAD]);
   g[L_ENC_HEAD].act = ACT_NONE; g[L_ENC_HEAD].out_f32 = pl->head;
+  if (full) return build_plan_full(h, pl, out);
   // ---- decoder (IAN_simple.py:129-170)
   set_io(g[L_DEC_FC2], pl->zp, n, 1, 1, 128, 1, 1, h->w[L_DEC_FC2], 1, 1); taps_dense(g[L_DEC_FC2]);
   g[L_DEC_FC2].act = ACT_RELU; g[L_DEC_FC2].out = pl->h0.p; g[L_DEC_FC2].out_plane = pl->h0.plane;
@@ -305,7 +451,7 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
   g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
 
-  for (int l = 0; l < L_COUNT; ++l) {
+  for (int l = 0; l < F_DEC_FC2; ++l) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
     if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
@@ -331,8 +477,8 @@ void free_plan(Plan* pl) {
     if (pl->ev_comp[s]) cudaEventDestroy(pl->ev_comp[s]);
     if (pl->ev_d2h[s]) cudaEventDestroy(pl->ev_d2h[s]);
   }
-  for (int l = 0; l < L_COUNT; ++l) tc_free_maps(pl->maps[l]);
-  decout_free_maps(pl->decout_maps);
+  for (int l = 0; l < L_COUNT; ++l) if (pl->maps[l]) tc_free_maps(pl->maps[l]);
+  if (pl->decout_maps) decout_free_maps(pl->decout_maps);
   delete pl;
 }
 
@@ -361,7 +507,6 @@ struct ScopedTimer {
 
 int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
-  g.tc_merged = h->tc_merged;
   ian_handle::Timed tm{};
   if (h->timing) {
     CUDA_TRY(h, cudaEventCreate(&tm.e0));
@@ -394,6 +539,12 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
   int rc;
   for (int l : {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  if (h->model_kind == IAN_MODEL_FULL) {
+    // l_Z_IAF = mu (+ exp(ls) eps), then l_Z = IAF(l_Z_IAF; MADE_mu, MADE_ls)   (IAN.py:126-128)
+    LAUNCH_TRY(h, launch_sample(pl->head, eps, pl->z0, nullptr, 0, n, st));
+    LAUNCH_TRY(h, launch_made_iaf(pl->z0, h->made_w, h->made_b, z, pl->zp.p, pl->zp.plane, n, st));
+    return IAN_OK;
+  }
   LAUNCH_TRY(h, launch_sample(pl->head, eps, z, pl->zp.p, pl->zp.plane, n, st));
   return IAN_OK;
 }
@@ -401,6 +552,12 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
 // zp must already hold the latent planes
 int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
   int rc;
+  if (h->model_kind == IAN_MODEL_FULL) {
+    for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD})
+      if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+    LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
+    return IAN_OK;
+  }
   for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
   ScopedTimer tm(h, T_DEC_OUT, st);
@@ -425,6 +582,12 @@ int run_grad_core(ian_handle* h, Plan* pl, const int32_t* boxes, const float* ta
                                       pl->h3.p, pl->d3.p, pl->d3.plane, pl->n, st));
   for (int l : {L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+  return IAN_OK;
+}
+
+int check_brush_supported(ian_handle* h) {
+  if (h && h->model_kind != IAN_MODEL_SIMPLE)
+    return fail(h, IAN_ERR_UNSUPPORTED, "brush gradients are implemented for the IAN_simple graph only (what NPE.py loads)");
   return IAN_OK;
 }
 
@@ -484,7 +647,7 @@ void fold_bn(ian_handle* h, const std::string& name, int c, std::vector<float>& 
   }
 }
 
-int prepare_simple(ian_handle* h) {
+int prepare_encoder(ian_handle* h) {
   int rc;
   std::vector<float> B, sc, sf;
   // enc_conv2..4: B[i*5+j][o][c] = W[o][c][i][j]
@@ -532,6 +695,32 @@ int prepare_simple(ian_handle* h) {
     for (int o = 0; o < 100; ++o) { sc[o] = s1[o]; sf[o] = f1[o]; sc[100 + o] = s2[o]; sf[100 + o] = f2[o]; }
     if ((rc = upload_gemm_weights(h, L_ENC_HEAD, B, 1, 256, 1024, sc, sf)) != IAN_OK) return rc;
   }
+  // conv1: wt[(c*5+i)*5+j][o] = W[o][c][i][j]
+  {
+    const auto& W = P(h, "enc_conv1.W").data;
+    std::vector<float> wt(75 * 128);
+    for (int o = 0; o < 128; ++o)
+      for (int k = 0; k < 75; ++k) wt[k * 128 + o] = W[o * 75 + k];
+    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_wt, wt.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->conv1_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    const auto& b = P(h, "enc_conv1.b").data;
+    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_b, 128 * 4));
+    CUDA_TRY(h, cudaMemcpy(h->conv1_b, b.data(), 128 * 4, cudaMemcpyHostToDevice));
+  }
+  return IAN_OK;
+}
+
+// 5x5 stride-2 transposed conv weights W (Cin,Cout,5,5) -> forward tiles B[k][co][ci] = W[ci][co][k]
+void deconv_fwd_tiles(const std::vector<float>& W, int Cin, int Cout, std::vector<float>& B) {
+  B.assign((size_t)25 * Cout * Cin, 0.f);
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int co = 0; co < Cout; ++co)
+      for (int t = 0; t < 25; ++t) B[((size_t)t * Cout + co) * Cin + ci] = W[((size_t)ci * Cout + co) * 25 + t];
+}
+
+int prepare_simple_decoder(ian_handle* h) {
+  int rc;
+  std::vector<float> B, sc, sf;
   // l_dec_fc2: reference column j = c*16 + hw -> our column hw*1024 + c; Cin 100 -> 128
   std::vector<float> sc0, sf0;
   {
@@ -581,18 +770,6 @@ int prepare_simple(ian_handle* h) {
     if ((rc = upload_gemm_weights(h, d.lb, B, 25, d.Cin, d.Cout, prev_scale, {})) != IAN_OK) return rc;
     prev_scale = sc;
   }
-  // conv1: wt[(c*5+i)*5+j][o] = W[o][c][i][j]
-  {
-    const auto& W = P(h, "enc_conv1.W").data;
-    std::vector<float> wt(75 * 128);
-    for (int o = 0; o < 128; ++o)
-      for (int k = 0; k < 75; ++k) wt[k * 128 + o] = W[o * 75 + k];
-    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_wt, wt.size() * 4));
-    CUDA_TRY(h, cudaMemcpy(h->conv1_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
-    const auto& b = P(h, "enc_conv1.b").data;
-    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_b, 128 * 4));
-    CUDA_TRY(h, cudaMemcpy(h->conv1_b, b.data(), 128 * 4, cudaMemcpyHostToDevice));
-  }
   // dec_out: wt[ki*5+kj][ci][co(4)] = W[ci][co][ki][kj]
   {
     const auto& W = P(h, "dec_out.W").data;
@@ -616,6 +793,133 @@ int prepare_simple(ian_handle* h) {
         for (int t = 0; t < 25; ++t) wt[(t * 128 + ci) * 4 + co] = W[(ci * 3 + co) * 25 + t];
     CUDA_TRY(h, cudaMalloc((void**)&h->decout_wt, wt.size() * 4));
     CUDA_TRY(h, cudaMemcpy(h->decout_wt, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return IAN_OK;
+}
+
+// composite MDC weights (reference layers.py:207-258): per distinct offset one [F][C] matrix
+//   base 3x3: W[f,c,i,j]*coeff_base[f] at (i-1, j-1);  scale 0: mean_ij(W)*coeff_1x1[f] at (0,0);
+//   scale s: W[f,c,i,j]*coeff_s[f] at ((i-1)s, (j-1)s)
+void mdc_composite(ian_handle* h, const std::string& name, int F, int C, const std::vector<int>& scales,
+                   std::vector<float>& comp /*[ntaps][F][C]*/) {
+  const auto off = mdc_offsets(scales);
+  const auto& W = P(h, (name + "W").c_str()).data;
+  comp.assign(off.size() * (size_t)F * C, 0.f);
+  auto tile_of = [&](int dy, int dx) { for (size_t t = 0; t < off.size(); ++t) if (off[t].first == dy && off[t].second == dx) return (int)t; return -1; };
+  auto put = [&](int s, const std::vector<float>& coeff) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const int t = tile_of((i - 1) * s, (j - 1) * s);
+        for (int f = 0; f < F; ++f)
+          for (int c = 0; c < C; ++c) comp[((size_t)t * F + f) * C + c] += W[(((size_t)f * C + c) * 3 + i) * 3 + j] * coeff[f];
+      }
+  };
+  put(1, P(h, (name + "_coeff_base").c_str()).data);
+  for (int s : scales) {
+    if (s == 0) {
+      const auto& coeff = P(h, (name + "_coeff_1x1").c_str()).data;
+      const int t = tile_of(0, 0);
+      for (int f = 0; f < F; ++f)
+        for (int c = 0; c < C; ++c) {
+          float m = 0.f;
+          for (int k = 0; k < 9; ++k) m += W[((size_t)f * C + c) * 9 + k];
+          comp[((size_t)t * F + f) * C + c] += (m / 9.f) * coeff[f];
+        }
+    } else {
+      put(s, P(h, (name + "_coeff_" + std::to_string(s)).c_str()).data);
+    }
+  }
+}
+
+int prepare_full_decoder(ian_handle* h) {
+  int rc;
+  std::vector<float> B, sc, sf, comp;
+  // ---- MADE (layers.py:653-853): masks from the ordering (mask_generator.py:93-94), integer
+  // comparisons, multiplied into the float32 weights here on the host (bit-exact W*M)
+  {
+    if (h->made_ordering.size() != 100) return fail(h, IAN_ERR_STATE, "ian_set_made_ordering() must precede ian_finalize() for the full IAN");
+    const auto& o = h->made_ordering;
+    std::vector<float> mw(2 * 3 * 10000), mb(2 * 3 * 100);
+    const char* nets[2] = {"l_IAF_mu", "l_IAF_ls"};
+    const char* subs[3] = {"_input", "_output_W", "_output_D"};
+    for (int net = 0; net < 2; ++net)
+      for (int m = 0; m < 3; ++m) {
+        const auto& W = P(h, (std::string(nets[net]) + subs[m] + ".W").c_str()).data;
+        const auto& b = P(h, (std::string(nets[net]) + subs[m] + ".b").c_str()).data;
+        for (int i = 0; i < 100; ++i)
+          for (int j = 0; j < 100; ++j) {
+            // connectivity: input = o+1, hidden = 1, output = o
+            const bool keep = m == 0 ? (o[i] + 1 <= 1) : m == 1 ? (1 <= o[j]) : (o[i] + 1 <= o[j]);
+            mw[((net * 3 + m) * 100 + i) * 100 + j] = keep ? W[i * 100 + j] : 0.f;
+          }
+        for (int j = 0; j < 100; ++j) mb[(net * 3 + m) * 100 + j] = b[j];
+      }
+    CUDA_TRY(h, cudaMalloc((void**)&h->made_w, mw.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->made_w, mw.data(), mw.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMalloc((void**)&h->made_b, mb.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->made_b, mb.data(), mb.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // ---- l_dec_fc2: dense 100 -> 8192 + bias, lrelu (IAN.py:129-134); column j = c*16+hw -> hw*512 + c
+  {
+    const auto& W = P(h, "l_dec_fc2.W").data;
+    const auto& b = P(h, "l_dec_fc2.b").data;
+    B.assign((size_t)8192 * 128, 0.f);
+    sc.assign(8192, 1.f);
+    sf.assign(8192, 0.f);
+    for (int c = 0; c < 512; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 512 + c;
+        sf[col] = b[j];
+        for (int k = 0; k < 100; ++k) B[(size_t)col * 128 + k] = W[(size_t)k * 8192 + j];
+      }
+    if ((rc = upload_gemm_weights(h, F_DEC_FC2, B, 1, 8192, 128, sc, sf)) != IAN_OK) return rc;
+  }
+  // ---- deconvs + MDBLOCKs (IAN.py:139-171)
+  struct St { int dconv, mda, mdb; const char* w; const char* blk; int Cin, Cout; std::vector<int> scales; };
+  const St sts[3] = {{F_DEC_CONV1, F_MD1A, F_MD1B, "dec_conv1.W", "dec_conv2a", 512, 512, {0, 2}},
+                     {F_DEC_CONV2, F_MD2A, F_MD2B, "dec_conv2.W", "dec_conv3a", 512, 256, {0, 2, 3}},
+                     {F_DEC_CONV3, F_MD3A, F_MD3B, "dec_conv3.W", "dec_conv4a", 256, 128, {0, 2, 3}}};
+  for (const St& s : sts) {
+    deconv_fwd_tiles(P(h, s.w).data, s.Cin, s.Cout, B);
+    fold_bn(h, std::string(s.blk) + "bnorm0", s.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, s.dconv, B, 25, s.Cout, s.Cin, sc, sf)) != IAN_OK) return rc;
+    const int nt = (int)mdc_offsets(s.scales).size();
+    mdc_composite(h, s.blk, s.Cout, s.Cout, s.scales, comp);
+    fold_bn(h, std::string(s.blk) + "bnorm1", s.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, s.mda, comp, nt, s.Cout, s.Cout, sc, sf)) != IAN_OK) return rc;
+    mdc_composite(h, std::string(s.blk) + "2", s.Cout, s.Cout, s.scales, comp);
+    fold_bn(h, std::string(s.blk) + "bnorm2", s.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, s.mdb, comp, nt, s.Cout, s.Cout, sc, sf)) != IAN_OK) return rc;
+  }
+  deconv_fwd_tiles(P(h, "dec_conv4.W").data, 128, 128, B);
+  fold_bn(h, "bnorm_dc4", 128, sc, sf);
+  if ((rc = upload_gemm_weights(h, F_DEC_CONV4, B, 25, 128, 128, sc, sf)) != IAN_OK) return rc;
+  // ---- RGB-Beta head (IAN.py:183-207): the three 128->2 MDC convs as one 16-row tile [R | G_a | B_a | 0...]
+  {
+    const std::vector<int> hs = {2, 3, 4};
+    const auto off = mdc_offsets(hs);
+    const int nt = (int)off.size();
+    B.assign((size_t)nt * 16 * 128, 0.f);
+    const char* names[3] = {"R", "G_a", "B_a"};
+    for (int k = 0; k < 3; ++k) {
+      mdc_composite(h, names[k], 2, 128, hs, comp);
+      for (int t = 0; t < nt; ++t)
+        for (int f = 0; f < 2; ++f)
+          for (int c = 0; c < 128; ++c) B[((size_t)t * 16 + 2 * k + f) * 128 + c] = comp[((size_t)t * 2 + f) * 128 + c];
+    }
+    sc.assign(16, 1.f);
+    if ((rc = upload_gemm_weights(h, F_HEAD, B, nt, 16, 128, sc, {})) != IAN_OK) return rc;
+    std::vector<int> taps(nt * 2);
+    for (int t = 0; t < nt; ++t) { taps[2 * t] = off[t].first; taps[2 * t + 1] = off[t].second; }
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_taps, taps.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+    h->head_ntaps = nt;
+    mdc_composite(h, "G_b", 2, 2, hs, comp);             // [nt][2 out][2 in]
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_wgb, comp.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_wgb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
+    mdc_composite(h, "B_b", 2, 4, hs, comp);             // [nt][2 out][4 in]
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_wbb, comp.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_wbb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
   }
   return IAN_OK;
 }
@@ -647,7 +951,8 @@ extern "C" {
 
 int ian_create(int model_kind, int device, ian_handle** out) {
   if (!out) return fail(nullptr, IAN_ERR_INVALID, "out is NULL");
-  if (model_kind != IAN_MODEL_SIMPLE) return fail(nullptr, IAN_ERR_UNSUPPORTED, "unknown model kind %d", model_kind);
+  if (model_kind != IAN_MODEL_SIMPLE && model_kind != IAN_MODEL_FULL)
+    return fail(nullptr, IAN_ERR_UNSUPPORTED, "unknown model kind %d", model_kind);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -669,7 +974,6 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   }
   if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
-  if (const char* c = getenv("IAN_TC_MERGED")) h->tc_merged = atoi(c) != 0;
   *out = h;
   return IAN_OK;
 }
@@ -677,19 +981,12 @@ int ian_create(int model_kind, int device, ian_handle** out) {
 int ian_set_param(ian_handle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
   if (!h || !name || !data || !shape) return fail(h, IAN_ERR_INVALID, "NULL argument");
   if (h->finalized) return fail(h, IAN_ERR_STATE, "model already finalized");
-  const ParamSpec* spec = nullptr;
-  ParamSpec bn_spec;
-  for (const auto& s : kSimpleWeights)
-    if (!strcmp(s.name, name)) spec = &s;
-  if (!spec) {
-    for (const auto& b : kSimpleBn)
-      for (const char* f : kBnFields) {
-        std::string full = std::string(b.name) + "." + f;
-        if (full == name) { bn_spec = {name, 1, {b.c}}; spec = &bn_spec; }
-      }
-  }
+  const std::vector<Spec> specs = spec_list(h->model_kind);
+  const Spec* spec = nullptr;
+  for (const auto& sp : specs)
+    if (sp.name == name) spec = &sp;
   if (!spec) return fail(h, IAN_ERR_INVALID, "unknown parameter name '%s'", name);
-  if (ndim != spec->ndim) return fail(h, IAN_ERR_INVALID, "parameter %s: expected %d dims, got %d", name, spec->ndim, ndim);
+  if (ndim != (int)spec->shape.size()) return fail(h, IAN_ERR_INVALID, "parameter %s: expected %d dims, got %d", name, (int)spec->shape.size(), ndim);
   int64_t elems = 1;
   for (int i = 0; i < ndim; ++i) {
     if (shape[i] != spec->shape[i])
@@ -703,18 +1000,28 @@ int ian_set_param(ian_handle* h, const char* name, const float* data, const int6
   return IAN_OK;
 }
 
+int ian_set_made_ordering(ian_handle* h, const int32_t* ordering, int n) {
+  if (!h || !ordering) return fail(h, IAN_ERR_INVALID, "NULL argument");
+  if (h->finalized) return fail(h, IAN_ERR_STATE, "model already finalized");
+  if (n != 100) return fail(h, IAN_ERR_INVALID, "ordering must have 100 entries (got %d)", n);
+  std::vector<char> seen(100, 0);
+  for (int i = 0; i < n; ++i) {
+    if (ordering[i] < 0 || ordering[i] >= 100 || seen[ordering[i]]) return fail(h, IAN_ERR_INVALID, "ordering is not a permutation of 0..99");
+    seen[ordering[i]] = 1;
+  }
+  h->made_ordering.assign(ordering, ordering + n);
+  return IAN_OK;
+}
+
 int ian_finalize(ian_handle* h) {
   if (!h) return IAN_ERR_INVALID;
   if (h->finalized) return IAN_OK;
-  for (const auto& s : kSimpleWeights)
-    if (!h->params.count(s.name)) return fail(h, IAN_ERR_STATE, "missing parameter '%s'", s.name);
-  for (const auto& b : kSimpleBn)
-    for (const char* f : kBnFields) {
-      std::string full = std::string(b.name) + "." + f;
-      if (!h->params.count(full)) return fail(h, IAN_ERR_STATE, "missing parameter '%s'", full.c_str());
-    }
+  for (const auto& sp : spec_list(h->model_kind))
+    if (!h->params.count(sp.name)) return fail(h, IAN_ERR_STATE, "missing parameter '%s'", sp.name.c_str());
   DeviceGuard dg(h->device);
-  int rc = prepare_simple(h);
+  int rc = prepare_encoder(h);
+  if (rc != IAN_OK) return rc;
+  rc = h->model_kind == IAN_MODEL_FULL ? prepare_full_decoder(h) : prepare_simple_decoder(h);
   if (rc != IAN_OK) return rc;
   h->params.clear();
   h->finalized = true;
@@ -730,6 +1037,7 @@ int ian_destroy(ian_handle* h) {
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
   cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
+  cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (void* p : h->host_allocs) cudaFreeHost(p);
   cudaStreamDestroy(h->stream);
@@ -872,6 +1180,7 @@ int ian_grad_dev(ian_handle* h, const float* z, const int32_t* boxes, const floa
                  float* g, void* stream) {
   int rc = check_ready(h, n, z, g);
   if (rc != IAN_OK) return rc;
+  if ((rc = check_brush_supported(h)) != IAN_OK) return rc;
   if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
   DeviceGuard dg(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -889,6 +1198,7 @@ int ian_grad_host(ian_handle* h, const float* z, const int32_t* boxes, const flo
                   float* g) {
   int rc = check_ready(h, n, z, g);
   if (rc != IAN_OK) return rc;
+  if ((rc = check_brush_supported(h)) != IAN_OK) return rc;
   if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
   if ((rc = validate_boxes(h, boxes, n)) != IAN_OK) return rc;
   DeviceGuard dg(h->device);
@@ -915,6 +1225,7 @@ int ian_edit_loop_dev(ian_handle* h, float* z, const int32_t* boxes, const float
                       int n_steps, float weight, void* stream) {
   int rc = check_ready(h, n, z, z);
   if (rc != IAN_OK) return rc;
+  if ((rc = check_brush_supported(h)) != IAN_OK) return rc;
   if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
   if (n_steps < 0) return fail(h, IAN_ERR_INVALID, "n_steps < 0");
   DeviceGuard dg(h->device);
@@ -936,6 +1247,7 @@ int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const floa
                        int n_steps, float weight) {
   int rc = check_ready(h, n, z, z);
   if (rc != IAN_OK) return rc;
+  if ((rc = check_brush_supported(h)) != IAN_OK) return rc;
   if (!boxes) return fail(h, IAN_ERR_INVALID, "boxes is NULL");
   if ((rc = validate_boxes(h, boxes, n)) != IAN_OK) return rc;
   DeviceGuard dg(h->device);

@@ -48,7 +48,7 @@ struct TapGemm {
   // B: [wtile][Cout][Cin] split planes, K(=Cin)-major
   const __nv_bfloat16* b;
   long long b_plane;
-  int Cout;                     // % 64 == 0 (padded by the host)
+  int Cout;                     // % 64 == 0 (padded by the host); 16 for the 2-filter RGB-Beta head convs
   int nphase;
   Phase phase[kMaxPhases];
   Tap taps[kMaxTaps];
@@ -67,7 +67,12 @@ struct TapGemm {
   // finalize kernel applies the epilogue.
   int ksplit;
   float* ws;
-  int tc_merged;                // 1: cross terms accumulate into the main TMEM accumulator (frees a 2nd buffer)
+  // MDBLOCK support (reference layers.py:411-416): `res` (output geometry, split planes) is added to the sum
+  // before scale/shift; `out_raw` receives the un-normalised sum (the block's residual input x)
+  const __nv_bfloat16* res;
+  long long res_plane;
+  __nv_bfloat16* out_raw;
+  long long out_raw_plane;
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {

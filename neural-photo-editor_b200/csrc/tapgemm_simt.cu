@@ -8,7 +8,7 @@ namespace ian {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 64, BN = 64, BK = 16;   // Cout may be 16 (RGB-Beta head): columns >= Cout are masked
 
 __device__ __forceinline__ float4 load_join4(const __nv_bfloat16* hi, long long plane) {
   // 4 consecutive channels: hi and lo planes, 8 bytes each
@@ -27,6 +27,13 @@ __device__ __forceinline__ void epilogue_store(const TapGemm& g, float acc, long
   int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
   float sc = g.scale ? g.scale[si] : 1.f;
   float v;
+  if (g.out_raw) {
+    __nv_bfloat16 rh, rl;
+    split_bf16(acc, rh, rl);
+    g.out_raw[pix * g.Cout + co] = rh;
+    g.out_raw[g.out_raw_plane + pix * g.Cout + co] = rl;
+  }
+  if (g.res) acc += __bfloat162float(g.res[pix * g.Cout + co]) + __bfloat162float(g.res[g.res_plane + pix * g.Cout + co]);
   if (g.act == ACT_MASK) {
     float mk = __bfloat162float(g.mask[pix * g.Cout + co]);
     v = mk > 0.f ? acc * sc : 0.f;
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
         g.b + ((long long)tap.wtile * g.Cout + (n0 + lr)) * g.Cin + lc;
     for (int c0 = 0; c0 < g.Cin; c0 += BK) {
       float4 av = ok ? load_join4(arow + c0, g.a_plane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 bv = load_join4(brow + c0, g.b_plane);
+      float4 bv = (n0 + lr < g.Cout) ? load_join4(brow + c0, g.b_plane) : make_float4(0.f, 0.f, 0.f, 0.f);
       __syncthreads();
       As[lc + 0][lr] = av.x; As[lc + 1][lr] = av.y; As[lc + 2][lr] = av.z; As[lc + 3][lr] = av.w;
       Bs[lc + 0][lr] = bv.x; Bs[lc + 1][lr] = bv.y; Bs[lc + 2][lr] = bv.z; Bs[lc + 3][lr] = bv.w;
@@ -107,6 +114,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
     const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
     const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
     const int co = n0 + tx * 4;
+    if (co >= g.Cout) continue;
     __align__(8) __nv_bfloat16 hi4[4], lo4[4];
     __align__(16) float f4[4];
 #pragma unroll
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_const
 
 int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st) {
   const int M = g.n_img * g.Hg * g.Wg;
-  dim3 grid((M + BM - 1) / BM, g.Cout / BN, g.nphase);
+  dim3 grid((M + BM - 1) / BM, (g.Cout + BN - 1) / BN, g.nphase);
   tapgemm_simt_kernel<<<grid, 256, 0, st>>>(g);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -43,12 +43,12 @@ constexpr int kATileBytes = BM * BK * 2 * 2;            // hi + lo planes: 32 KB
 
 constexpr int kEpiWarps = 8;
 
-template <int BN, bool MERGED> struct TcCfg {
+template <int BN> struct TcCfg {
   static constexpr int kBTileBytes = BN * BK * 2 * 2;  // hi + lo
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStagesFit = (196 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kAccCols = MERGED ? BN : 2 * BN;        // TMEM columns of one accumulator buffer
+  static constexpr int kAccCols = 2 * BN;                      // TMEM columns of one buffer: main | cross
   static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (kAccBufs * kAccCols <= 32) ? 32 : (kAccBufs * kAccCols <= 64) ? 64 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 256;
@@ -65,6 +65,21 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { r
 struct WorkItem {
   int phase, ks, n0, p0, q0, co0, it0, it1;
 };
+
+// CH float32 values -> bf16 hi|lo planes, 16-byte stores
+template <int CH>
+__device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane, const float (&v)[CH]) {
+  __align__(16) __nv_bfloat16 hi[CH], lo[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) split_bf16(v[j], hi[j], lo[j]);
+  uint4* oh4 = reinterpret_cast<uint4*>(dst);
+  uint4* ol4 = reinterpret_cast<uint4*>(dst + plane);
+#pragma unroll
+  for (int j = 0; j < CH / 8; ++j) {
+    oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
+    ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+  }
+}
 
 template <int BN>
 __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& maps, int w) {
@@ -88,10 +103,10 @@ __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& 
   return wi;
 }
 
-template <int BN, bool MERGED>
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
-  using Cfg = TcCfg<BN, MERGED>;
+  using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -155,7 +170,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
         const WorkItem wi = decode_work<BN>(g, maps, w);
         const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
         const uint32_t acc_main = tmem_base + buf * Cfg::kAccCols;
-        const uint32_t acc_cross = MERGED ? acc_main : acc_main + BN;
+        const uint32_t acc_cross = acc_main + BN;
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained this buffer
         tc_fence_after();
         for (int it = wi.it0; it < wi.it1; ++it, ++i) {
@@ -172,7 +187,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes per K=16 slice, in 16-byte units
             const uint32_t acc = (!first || k > 0) ? 1u : 0u;
             umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, MERGED ? 1u : acc);
+            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
             umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
           }
           umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
@@ -214,19 +229,12 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           float v[CH];
           __syncwarp();                                 // tcgen05.ld is .aligned: reconverge first
           {
-            uint32_t vm[CH];
+            uint32_t vm[CH], vc[CH];
             tmem_ld<CH>(lane_addr + cb, vm);
-            if (!MERGED) {
-              uint32_t vc[CH];
-              tmem_ld<CH>(lane_addr + BN + cb, vc);
-              tmem_ld_wait();
+            tmem_ld<CH>(lane_addr + BN + cb, vc);
+            tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
-            } else {
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]);
-            }
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
           }
           if (cc + CH >= COLS_PER_WARP) {               // last TMEM read of this work item: release the buffer
             tc_fence_before();
@@ -251,9 +259,23 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             __syncwarp();
           }
           if (valid) {
+            const long long off = pix * g.Cout + co;
+            if (g.out_raw) store_split<CH>(g.out_raw + off, g.out_raw_plane, v);   // pre-BN value (MDBLOCK residual input)
+            if (g.res) {                                   // residual add before BatchNorm (MDBLOCK, layers.py:411-416)
+              const uint4* rh = reinterpret_cast<const uint4*>(g.res + off);
+              const uint4* rl = reinterpret_cast<const uint4*>(g.res + g.res_plane + off);
+#pragma unroll
+              for (int j8 = 0; j8 < CH / 8; ++j8) {
+                const uint4 h4 = __ldg(rh + j8), l4 = __ldg(rl + j8);
+                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h4);
+                const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
+              }
+            }
             if (g.act == ACT_MASK) {
               const int si = co + (oh * g.Wout + ow) * g.scale_pix_stride;
-              const uint4* mk = reinterpret_cast<const uint4*>(g.mask + pix * g.Cout + co);
+              const uint4* mk = reinterpret_cast<const uint4*>(g.mask + off);
 #pragma unroll
               for (int j8 = 0; j8 < CH / 8; ++j8) {
                 const uint4 m4 = __ldg(mk + j8);
@@ -275,20 +297,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
                 v[4 * j4 + 3] = act_apply(fmaf(v[4 * j4 + 3], sc.w, sf.w), g.act);
               }
             }
-            if (g.out) {
-              __align__(16) __nv_bfloat16 hi[CH], lo[CH];
-#pragma unroll
-              for (int j = 0; j < CH; ++j) split_bf16(v[j], hi[j], lo[j]);
-              uint4* oh4 = reinterpret_cast<uint4*>(g.out + pix * g.Cout + co);
-              uint4* ol4 = reinterpret_cast<uint4*>(g.out + g.out_plane + pix * g.Cout + co);
-#pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
-                ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
-              }
-            }
+            if (g.out) store_split<CH>(g.out + off, g.out_plane, v);
             if (g.out_f32) {
-              float4* of = reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co);
+              float4* of = reinterpret_cast<float4*>(g.out_f32 + off);
 #pragma unroll
               for (int j = 0; j < CH / 4; ++j) of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
@@ -312,13 +323,13 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
 TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
   tc::EncodeTiledFn enc = tc::get_encode_fn();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return nullptr; }
-  if (g.Cin % 64 || g.Cout % 128) { snprintf(err, errlen, "tc path needs Cin%%64==0 and Cout%%128==0 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
+  if (g.Cin % 64 || (g.Cout % 128 && g.Cout != 16)) { snprintf(err, errlen, "tc path needs Cin%%64==0 and Cout%%128==0 or Cout==16 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
   TcMaps* m = new TcMaps();
   memset(m, 0, sizeof(*m));
   m->Wt = g.Wg < BM ? g.Wg : BM;
   m->Ht = g.Hg < BM / m->Wt ? g.Hg : BM / m->Wt;
   m->Nt = BM / (m->Wt * m->Ht);
-  m->BN = (g.Cout % 256 == 0) ? 256 : 128;
+  m->BN = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
   if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
     snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
     delete m; return nullptr;
@@ -364,16 +375,16 @@ void tc_free_maps(TcMaps* m) { delete m; }
 
 int tc_tile_width(const TcMaps* maps) { return maps->BN; }
 
-template <int BN, bool MERGED>
+template <int BN>
 static int launch_one(const TapGemm& g, const TcMaps* maps, int total_work, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, MERGED>;
+  using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
     attr_set = true;
   }
-  tapgemm_tc_kernel<BN, MERGED><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  tapgemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -387,8 +398,9 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
   const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
   const int total_work = tiles_m * (g.Cout / maps->BN) * g.nphase * g.ksplit;
   const int grid = total_work < num_sms ? total_work : num_sms;
-  if (maps->BN == 256) return g.tc_merged ? launch_one<256, true>(g, maps, total_work, grid, st) : launch_one<256, false>(g, maps, total_work, grid, st);
-  return launch_one<128, false>(g, maps, total_work, grid, st);
+  if (maps->BN == 256) return launch_one<256>(g, maps, total_work, grid, st);
+  if (maps->BN == 128) return launch_one<128>(g, maps, total_work, grid, st);
+  return launch_one<16>(g, maps, total_work, grid, st);
 }
 
 }  // namespace ian

@@ -53,9 +53,19 @@ def test_input_filtering_matches_theano_rules(npe):
     assert api._f32(np.zeros((2, 100), np.float32), 2, "z").flags["C_CONTIGUOUS"]
 
 
-def test_only_simple_config_is_accepted(npe, weights):
+def test_unknown_config_is_rejected(npe, weights):
     with pytest.raises(NotImplementedError):
-        npe.IAN("IAN.py", True, weights=weights)
+        npe.IAN("IANv1.py", True, weights=weights)
+
+
+def test_made_ordering_host_logic_matches_oracle(npe):
+    """bit-exact MADE mask indexing starts from the same integer ordering on both sides."""
+    api = __import__("importlib").import_module("neural-photo-editor_b200.API")
+    from oracle import ian_full_numpy as fn
+    o = api.made_ordering()
+    assert o.dtype == np.int32 and sorted(o.tolist()) == list(range(100))
+    assert np.array_equal(o, fn.made_ordering().astype(np.int32))
+    assert o[:12].tolist() == [52, 79, 87, 45, 24, 71, 82, 80, 34, 36, 89, 77] and o[80] == 0
 
 
 def test_product_never_imports_oracle():
