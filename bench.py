@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-edit", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the full-IAN (BASELINE configs[2]) block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -343,6 +344,39 @@ def main():
                 "unit": "sample-steps/sec", "loop_iters_per_sec": EDIT_STEPS / (ems / 1e3), "ms_total": ems,
                 "tflops": 2.5625 * EDIT_BATCH * EDIT_STEPS / (ems / 1e3) / 1e3}
 
+    # ---- secondary block: full IAN (reference IAN.py graph), BASELINE configs[2] size (batch 512)
+    full = None
+    if not args.no_full and rank == 0:
+        fm = pkg.IAN("IAN.py", dnn=True, weights=ow.make_full_weights(0), device=local_rank)
+        FB = 512
+        xf = torch.from_numpy(np.random.default_rng(77).uniform(-1, 1, (FB, 3, 64, 64)).astype(np.float32)).to(dev)
+        zf = torch.empty(FB, 100, device=dev)
+        xhf = torch.empty(FB, 3, 64, 64, device=dev)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fsteps = max(3, args.steps // 6)
+        f0.record()
+        for _ in range(fsteps):
+            fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / fsteps
+        fm.set_layer_timing(True)
+        fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+        torch.cuda.synchronize()
+        fm.set_layer_timing(False)
+        names = ["enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "full_dec_fc2", "full_dec_conv1", "dec_conv2a",
+                 "dec_conv2a2", "full_dec_conv2", "dec_conv3a", "dec_conv3a2", "full_dec_conv3", "dec_conv4a", "dec_conv4a2",
+                 "full_dec_conv4", "rgb_head"]
+        full = {"metric": "64x64 images/sec full IAN (IAN.py) encode->decode @ batch 512", "value": FB / (fms / 1e3),
+                "unit": "images/sec", "ms_per_step": fms, "dtype": "f32 (3-pass bf16 split)",
+                "tflops_algorithmic": 7.9072 * FB / (fms / 1e3) / 1e3,
+                "layer_ms": {k: round(fm.layer_time_ms(k), 4) for k in names}}
+        fm.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_restatement_rate()
@@ -356,7 +390,7 @@ def main():
                            "l2": "no flush: one step streams 211 MB of weights + ~1 GB of activations (> 126 MB L2)",
                            "collective": "all_gather of decoded images" if world > 1 else "none"},
                 "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": sampler.summary(), "edit": edit}
+                "gpu_launches": launches, "clocks": sampler.summary(), "edit": edit, "full_ian": full}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

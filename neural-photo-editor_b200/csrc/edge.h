@@ -18,6 +18,7 @@ int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, f
 // full IAN: MADE+IAF latent flow and the autoregressive RGB-Beta head
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st);
+int launch_head_gather(const float* tt, const int* taps, int ntaps, float* ha, int n, cudaStream_t st);
 int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
                          float* xhat, int n, cudaStream_t st);
 // dec_out on the tensor-core path (decout_tc.cu)

@@ -212,7 +212,7 @@ struct Plan {
   int32_t* boxes = nullptr;
   // full IAN activations (NHWC split planes): block input x, pre-activated t0, mid t2, block output y per scale
   Planes fh0, fx1, ft1, fu1, fy1, fx2, ft2, fu2, fy2, fx3, ft3, fu3, fy3, fh4;
-  float *z0 = nullptr, *ha = nullptr, *rg = nullptr;
+  float *z0 = nullptr, *ha = nullptr, *rg = nullptr, *tt = nullptr;   // tt: head tap table [n][198][4096]
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
   DecOutMaps* decout_maps = nullptr;
@@ -322,7 +322,7 @@ void set_io(TapGemm& g, const Planes& a, int n, int Hin, int Win, int Cin, int H
   g.scale = w.scale; g.shift = w.shift; g.scale_pix_stride = 0;
   g.Hout = Hout; g.Wout = Wout;
   g.ksplit = 1; g.ws = nullptr; g.mask = nullptr; g.out = nullptr; g.out_f32 = nullptr; g.out_plane = 0;
-  g.res = nullptr; g.res_plane = 0; g.out_raw = nullptr; g.out_raw_plane = 0;
+  g.res = nullptr; g.res_plane = 0; g.out_raw = nullptr; g.out_raw_plane = 0; g.out_f32_t = nullptr; g.cout_real = 0;
 }
 
 int choose_ksplit(const TapGemm& g) {
@@ -381,8 +381,10 @@ int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
   }
   set_io(g[F_DEC_CONV4], pl->fy3, n, 32, 32, 128, 32, 32, h->w[F_DEC_CONV4], 64, 64); taps_deconv_s2(g[F_DEC_CONV4]);
   g[F_DEC_CONV4].act = ACT_LRELU; outp(g[F_DEC_CONV4], pl->fh4);
-  set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_mdc(g[F_HEAD], {2, 3, 4});
-  g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32 = pl->ha;
+  // RGB-Beta head: ONE dense 128 -> 33 taps x 6 filters GEMM (no shifts: the feature map is staged once, not 33
+  // times), written channel-major; the dilated taps are applied afterwards as coalesced shifted reads (head_gather)
+  set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
+  g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
   int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
                                F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD});
   if (rc != IAN_OK) return rc;
@@ -411,7 +413,7 @@ int build_plan(ian_handle* h, int n, Plan** out) {
     AP(fx2, N * 256 * 256) AP(ft2, N * 256 * 256) AP(fu2, N * 256 * 256) AP(fy2, N * 256 * 256)
     AP(fx3, N * 1024 * 128) AP(ft3, N * 1024 * 128) AP(fu3, N * 1024 * 128) AP(fy3, N * 1024 * 128)
     AP(fh4, N * 4096 * 128)
-    AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4)
+    AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4) AB(tt, N * 198 * 4096)
   }
 #undef AP
 #undef AB
@@ -555,6 +557,7 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   if (h->model_kind == IAN_MODEL_FULL) {
     for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
     LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
     return IAN_OK;
   }
@@ -899,16 +902,18 @@ int prepare_full_decoder(ian_handle* h) {
     const std::vector<int> hs = {2, 3, 4};
     const auto off = mdc_offsets(hs);
     const int nt = (int)off.size();
-    B.assign((size_t)nt * 16 * 128, 0.f);
+    if (nt * 6 != 198) return fail(h, IAN_ERR_STATE, "unexpected head tap count %d", nt);
+    // one weight tile [256 rows][128]: row t*6 + (2k+f) = composite tap t of filter f of conv k in {R, G_a, B_a}
+    B.assign((size_t)256 * 128, 0.f);
     const char* names[3] = {"R", "G_a", "B_a"};
     for (int k = 0; k < 3; ++k) {
       mdc_composite(h, names[k], 2, 128, hs, comp);
       for (int t = 0; t < nt; ++t)
         for (int f = 0; f < 2; ++f)
-          for (int c = 0; c < 128; ++c) B[((size_t)t * 16 + 2 * k + f) * 128 + c] = comp[((size_t)t * 2 + f) * 128 + c];
+          for (int c = 0; c < 128; ++c) B[((size_t)(t * 6 + 2 * k + f)) * 128 + c] = comp[((size_t)t * 2 + f) * 128 + c];
     }
-    sc.assign(16, 1.f);
-    if ((rc = upload_gemm_weights(h, F_HEAD, B, nt, 16, 128, sc, {})) != IAN_OK) return rc;
+    sc.assign(256, 1.f);
+    if ((rc = upload_gemm_weights(h, F_HEAD, B, 1, 256, 128, sc, {})) != IAN_OK) return rc;
     std::vector<int> taps(nt * 2);
     for (int t = 0; t < nt; ++t) { taps[2 * t] = off[t].first; taps[2 * t + 1] = off[t].second; }
     CUDA_TRY(h, cudaMalloc((void**)&h->head_taps, taps.size() * 4));

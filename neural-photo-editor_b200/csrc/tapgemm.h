@@ -73,6 +73,10 @@ struct TapGemm {
   long long res_plane;
   __nv_bfloat16* out_raw;
   long long out_raw_plane;
+  // channel-major float32 output [n][cout_real][Hout*Wout] (columns >= cout_real are dropped): coalesced when a
+  // warp's 32 rows are consecutive pixels; used for the RGB-Beta head's tap table
+  float* out_f32_t;
+  int cout_real;
 };
 
 __device__ __forceinline__ float act_apply(float v, int act) {

@@ -124,6 +124,12 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
       *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
     }
     if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co) = *reinterpret_cast<float4*>(f4);
+    if (g.out_f32_t) {
+      const long long hw = (long long)g.Hout * g.Wout;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co + j < g.cout_real) g.out_f32_t[((long long)n * g.cout_real + co + j) * hw + (long long)oh * g.Wout + ow] = f4[j];
+    }
   }
 }
 

@@ -298,6 +298,13 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
               }
             }
             if (g.out) store_split<CH>(g.out + off, g.out_plane, v);
+            if (g.out_f32_t) {                           // channel-major fp32: [n][co][Hout*Wout], lanes = consecutive pixels
+              const long long hw = (long long)g.Hout * g.Wout;
+              float* ot = g.out_f32_t + ((long long)n * g.cout_real + co) * hw + (long long)oh * g.Wout + ow;
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                if (co + j < g.cout_real) ot[j * hw] = v[j];
+            }
             if (g.out_f32) {
               float4* of = reinterpret_cast<float4*>(g.out_f32 + off);
 #pragma unroll

@@ -7,4 +7,5 @@ python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/bench_last.json').read())
 print("ms/step %.3f  img/s %.0f  e2e %.0f  edit %s" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["edit"] and round(d["edit"]["value"])), d["roofline"]["layer_ms"], d["roofline"]["edge_kernel_ms"], "frac %.3f" % d["roofline"]["frac"], "launches", d["gpu_launches"], d["clocks"])
+print("full_ian:", d.get("full_ian"))
 PY
