@@ -352,29 +352,36 @@ def main():
         xf = torch.from_numpy(np.random.default_rng(77).uniform(-1, 1, (FB, 3, 64, 64)).astype(np.float32)).to(dev)
         zf = torch.empty(FB, 100, device=dev)
         xhf = torch.empty(FB, 3, 64, 64, device=dev)
-        torch.cuda.synchronize()
-        for _ in range(3):
-            fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
-        torch.cuda.synchronize()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fsteps = max(3, args.steps // 6)
-        f0.record()
-        for _ in range(fsteps):
-            fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
-        f1.record()
-        torch.cuda.synchronize()
-        fms = f0.elapsed_time(f1) / fsteps
-        fm.set_layer_timing(True)
-        fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
-        torch.cuda.synchronize()
-        fm.set_layer_timing(False)
         names = ["enc_conv2", "enc_conv3", "enc_conv4", "enc_fc1", "enc_head", "full_dec_fc2", "full_dec_conv1", "dec_conv2a",
                  "dec_conv2a2", "full_dec_conv2", "dec_conv3a", "dec_conv3a2", "full_dec_conv3", "dec_conv4a", "dec_conv4a2",
                  "full_dec_conv4", "rgb_head"]
-        full = {"metric": "64x64 images/sec full IAN (IAN.py) encode->decode @ batch 512", "value": FB / (fms / 1e3),
-                "unit": "images/sec", "ms_per_step": fms, "dtype": "f32 (3-pass bf16 split)",
-                "tflops_algorithmic": 7.9072 * FB / (fms / 1e3) / 1e3,
-                "layer_ms": {k: round(fm.layer_time_ms(k), 4) for k in names}}
+        fsteps = max(3, args.steps // 6)
+        res, outs = {}, {}
+        for prec in ("fp32", "bf16"):
+            fm.set_precision(prec)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(fsteps):
+                fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / fsteps
+            fm.set_layer_timing(True)
+            fm.reconstruct_dev(xf.data_ptr(), FB, zf.data_ptr(), xhf.data_ptr(), stream)
+            torch.cuda.synchronize()
+            fm.set_layer_timing(False)
+            outs[prec] = xhf.clone()
+            res[prec] = {"value": FB / (fms / 1e3), "ms_per_step": fms, "tflops_algorithmic": 7.9072 * FB / (fms / 1e3) / 1e3,
+                         "layer_ms": {k: round(fm.layer_time_ms(k), 4) for k in names}}
+        diff = (outs["bf16"] - outs["fp32"]).abs()
+        full = {"metric": "64x64 images/sec full IAN (IAN.py) encode->decode @ batch 512 (BASELINE configs[2])",
+                "unit": "images/sec", "value": res["bf16"]["value"], "dtype": "bf16 operands, fp32 accumulate (single tcgen05 pass)",
+                "bf16": res["bf16"], "fp32_split": res["fp32"],
+                "bf16_vs_fp32_max_abs": float(diff.max().item()), "bf16_vs_fp32_mean_abs": float(diff.mean().item())}
         fm.close()
 
     cpu = None

@@ -77,6 +77,11 @@ const char* ian_last_error(const ian_handle* h);   /* h may be NULL: last error 
 
 int ian_get_zdim(const ian_handle* h);             /* replaces IAN.get_zdim (API.py:92-96) -> 100 */
 int ian_set_path(ian_handle* h, int path);         /* ian_path                                    */
+/* Arithmetic of the dense contractions.  IAN_PRECISION_FP32 (default): float32 semantics, every operand kept as
+ * bf16 hi|lo planes, 3 tensor-core passes.  IAN_PRECISION_BF16 (full IAN only; BASELINE configs[2]): operands
+ * rounded to bf16, one pass, fp32 accumulation -- about 1e-2 max-abs from the float32 result. */
+typedef enum ian_precision { IAN_PRECISION_FP32 = 0, IAN_PRECISION_BF16 = 1 } ian_precision;
+int ian_set_precision(ian_handle* h, int precision);
 /* Number of kernels this library launched on the handle since creation (bench.py gpu_launches). */
 int64_t ian_launch_count(const ian_handle* h);
 
@@ -107,6 +112,15 @@ int ian_reconstruct_wait(ian_handle* h, int ticket);
 /* Page-locked host memory owned by the handle (freed by ian_host_free or ian_destroy). */
 int ian_host_alloc(ian_handle* h, size_t bytes, void** out);
 int ian_host_free(ian_handle* h, void* p);
+
+/* ---- the function set of the reference's sampling script (reference sample_IAN.py:86-94) ---------------------
+ *   Zfn      : X -> l_Z_IAF (deterministic = mu, before the MADE/IAF flow)        -> ian_encode_pre_host
+ *   Z_IAF_fn : l_Z_IAF -> l_Z = (z - MADE_mu(z)) / exp(MADE_ls(z))                 -> ian_flow_host(z_out)
+ *   sample   : l_Z_IAF -> X (flow, then decoder)                                   -> ian_flow_host(x_out)
+ *   sampleZ  : l_Z -> X                                                            -> ian_decode_host
+ * For IAN_MODEL_SIMPLE there is no flow: Zfn == encode and Z_IAF_fn is the identity. */
+int ian_encode_pre_host(ian_handle* h, const float* x, int n, float* z_iaf);
+int ian_flow_host(ian_handle* h, const float* z_iaf, int n, float* z_out /*nullable*/, float* x_out /*nullable*/);
 
 /* ---- latent-brush gradients: replace calculate_RGB_gradient / calculate_lighten_gradient
  * (reference API.py:59, 64; IAN.imgrad / IAN.imgradRGB API.py:66-76), batched per sample -------- */

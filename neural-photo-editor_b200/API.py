@@ -139,6 +139,10 @@ class IAN:
         """'tc' (tcgen05, default) or 'simt' (fp32 FFMA verification path); both are CUDA."""
         self._check(self._lib.ian_set_path(self._h, {'tc': _lib.IAN_PATH_TC, 'simt': _lib.IAN_PATH_SIMT}[path]))
 
+    def set_precision(self, precision):
+        """'fp32' (default: float32 semantics via the 3-pass bf16 split) or 'bf16' (full IAN only, single pass)."""
+        self._check(self._lib.ian_set_precision(self._h, {'fp32': 0, 'bf16': 1}[precision]))
+
     def launch_count(self):
         return int(self._lib.ian_launch_count(self._h))
 
@@ -213,6 +217,47 @@ class IAN:
             e = None if eps is None else _f32(eps, 2, 'eps')
             self._check(self._lib.ian_encode_host(self._h, _fp(x), n, _fp(e) if e is not None else None, _fp(z)))
         return z
+
+    # ---- the reference sampling script's function set (sample_IAN.py:86-94) ---------------------------------
+    def Zfn(self, images):
+        """X -> l_Z_IAF, deterministic (= mu, before the MADE/IAF flow); sample_IAN.py:91."""
+        x = _f32(images, 4, 'images')
+        z = np.empty((x.shape[0], 100), np.float32)
+        if x.shape[0]:
+            self._check(self._lib.ian_encode_pre_host(self._h, _fp(x), x.shape[0], _fp(z)))
+        return z
+
+    def Z_IAF_fn(self, z_iaf):
+        """l_Z_IAF -> l_Z through the MADE/IAF flow (identity for IAN_simple); sample_IAN.py:94."""
+        z0 = _f32(z_iaf, 2, 'z')
+        z = np.empty_like(z0)
+        if z0.shape[0]:
+            self._check(self._lib.ian_flow_host(self._h, _fp(z0), z0.shape[0], _fp(z), None))
+        return z
+
+    def sample(self, z_iaf):
+        """l_Z_IAF -> X: flow, then decoder; sample_IAN.py:86 (what the script feeds N(0,1) noise to)."""
+        z0 = _f32(z_iaf, 2, 'z')
+        x = np.empty((z0.shape[0], 3, 64, 64), np.float32)
+        if z0.shape[0]:
+            self._check(self._lib.ian_flow_host(self._h, _fp(z0), z0.shape[0], None, _fp(x)))
+        return x
+
+    def sampleZ(self, z):
+        """l_Z -> X; sample_IAN.py:88 (== sample_at)."""
+        return self.sample_at(z)
+
+    def sample_grid(self, endpoints, n_samples=27, seed=None):
+        """The 6x9 grid of sample_IAN.py:173-187: n_samples random samples + 3 rows of [endpoint, 7 interpolants,
+        endpoint].  `endpoints`: 6 images float32 (6,3,64,64) in [-1,1].  Returns float32 images in [-1,1]."""
+        rng = np.random.RandomState(seed)
+        samples = self.sample(rng.randn(n_samples, 100).astype(np.float32))
+        ends = _f32(endpoints, 4, 'endpoints')
+        Ze = self.Zfn(ends)
+        Z = np.asarray([Ze[2 * i] * (1 - j) + Ze[2 * i + 1] * j for i in range(3) for j in [t / 6.0 for t in range(7)]],
+                       dtype=np.float32)
+        rows = [np.insert(ends[2 * i:2 * (i + 1)], 1, self.sample(Z[7 * i:7 * (i + 1)]), axis=0) for i in range(3)]
+        return np.append(samples, np.concatenate(rows, axis=0), axis=0)
 
     def reconstruct(self, images, return_z=False, out=None):
         """encode -> decode in one library call (the BASELINE metric's path).  `out`: optional preallocated

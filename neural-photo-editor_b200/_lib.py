@@ -26,6 +26,7 @@ SIGNATURES = {
     "ian_last_error": (C.c_char_p, [_H]),
     "ian_get_zdim": (C.c_int, [_H]),
     "ian_set_path": (C.c_int, [_H, C.c_int]),
+    "ian_set_precision": (C.c_int, [_H, C.c_int]),
     "ian_launch_count": (C.c_int64, [_H]),
     "ian_encode_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ian_encode_host": (C.c_int, [_H, _F, C.c_int, _F, _F]),
@@ -37,6 +38,8 @@ SIGNATURES = {
     "ian_reconstruct_wait": (C.c_int, [_H, C.c_int]),
     "ian_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ian_host_free": (C.c_int, [_H, C.c_void_p]),
+    "ian_encode_pre_host": (C.c_int, [_H, _F, C.c_int, _F]),
+    "ian_flow_host": (C.c_int, [_H, _F, C.c_int, _F, _F]),
     "ian_grad_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ian_grad_host": (C.c_int, [_H, _F, _I, _F, C.c_int, C.c_int, _F]),
     "ian_edit_loop_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -340,22 +340,23 @@ __global__ void __launch_bounds__(128) made_iaf_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// tt: [n][ntaps*6][4096] fp32, tt[n][t*6+f][pix] = sum_c h[pix][c] * Wc[t][f][c]  (one dense GEMM, no shifts).
-// ha[pix][f] = sum_t tt[n][t*6+f][pix + (dy_t, dx_t)]  -- the 33 dilated taps become 33 coalesced shifted reads.
+// tt: tap table of one dense GEMM (no shifts), tile-blocked: tt[(n*32 + p/2)][t*6+f][(p%2)*64 + q] =
+//     sum_c h[n,p,q,c] * Wc[t][f][c]       (a tile = 2 image rows, see TapGemm::out_f32_t)
+// ha[pix][f] = sum_t tt[..pix + (dy_t, dx_t)..][t*6+f]  -- the 33 dilated taps become 33 coalesced shifted reads.
 __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ tt, const int* __restrict__ taps, int ntaps,
                                                           float* __restrict__ ha, int n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
   const long long img = i >> 12;
-  const float* base = tt + img * ntaps * 6 * 4096;
+  const int ncol = ntaps * 6;
   float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int t = 0; t < ntaps; ++t) {
     const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
     if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
-    const float* src = base + (long long)t * 6 * 4096 + pp * 64 + qq;
+    const float* src = tt + ((img * 32 + (pp >> 1)) * ncol + t * 6) * 128 + (pp & 1) * 64 + qq;
 #pragma unroll
-    for (int f = 0; f < 6; ++f) a[f] += src[f * 4096];
+    for (int f = 0; f < 6; ++f) a[f] += src[f * 128];
   }
   float* o = ha + i * 16;
   *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);

@@ -146,6 +146,7 @@ struct ian_handle {
   int device = 0;
   int model_kind = 0;
   int path = IAN_PATH_TC;
+  int passes = 3;              // 3: float32 semantics (bf16 hi|lo split); 1: plain bf16 tensor-core math
   bool finalized = false;
   cudaStream_t stream = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined host API
@@ -509,6 +510,7 @@ struct ScopedTimer {
 
 int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
+  g.passes = h->passes;
   ian_handle::Timed tm{};
   if (h->timing) {
     CUDA_TRY(h, cudaEventCreate(&tm.e0));
@@ -532,7 +534,8 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   return IAN_OK;
 }
 
-int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float* z, cudaStream_t st) {
+// z_pre (nullable): the pre-flow latent l_Z_IAF (= z itself for IAN_simple)
+int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float* z, cudaStream_t st, float* z_pre = nullptr) {
   const int n = pl->n;
   {
     ScopedTimer tm(h, T_CONV1, st);
@@ -543,11 +546,12 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
   if (h->model_kind == IAN_MODEL_FULL) {
     // l_Z_IAF = mu (+ exp(ls) eps), then l_Z = IAF(l_Z_IAF; MADE_mu, MADE_ls)   (IAN.py:126-128)
-    LAUNCH_TRY(h, launch_sample(pl->head, eps, pl->z0, nullptr, 0, n, st));
-    LAUNCH_TRY(h, launch_made_iaf(pl->z0, h->made_w, h->made_b, z, pl->zp.p, pl->zp.plane, n, st));
+    LAUNCH_TRY(h, launch_sample(pl->head, eps, z_pre ? z_pre : pl->z0, nullptr, 0, n, st));
+    LAUNCH_TRY(h, launch_made_iaf(z_pre ? z_pre : pl->z0, h->made_w, h->made_b, z, pl->zp.p, pl->zp.plane, n, st));
     return IAN_OK;
   }
   LAUNCH_TRY(h, launch_sample(pl->head, eps, z, pl->zp.p, pl->zp.plane, n, st));
+  if (z_pre) CUDA_TRY(h, cudaMemcpyAsync(z_pre, z, (size_t)n * 400, cudaMemcpyDeviceToDevice, st));
   return IAN_OK;
 }
 
@@ -1063,6 +1067,15 @@ int ian_set_path(ian_handle* h, int path) {
   return IAN_OK;
 }
 
+int ian_set_precision(ian_handle* h, int precision) {
+  if (!h) return IAN_ERR_INVALID;
+  if (precision != IAN_PRECISION_FP32 && precision != IAN_PRECISION_BF16) return fail(h, IAN_ERR_INVALID, "unknown precision %d", precision);
+  if (precision == IAN_PRECISION_BF16 && h->model_kind != IAN_MODEL_FULL)
+    return fail(h, IAN_ERR_UNSUPPORTED, "bf16 mode is built for the full IAN graph (BASELINE configs[2]); IAN_simple runs in float32");
+  h->passes = precision == IAN_PRECISION_BF16 ? 1 : 3;
+  return IAN_OK;
+}
+
 int ian_set_layer_timing(ian_handle* h, int enable) {
   if (!h) return IAN_ERR_INVALID;
   h->timing = enable != 0;
@@ -1344,6 +1357,54 @@ int ian_reconstruct_wait(ian_handle* h, int ticket) {
   if (it == h->plans.end() || !it->second->ev_d2h[s]) return fail(h, IAN_ERR_INVALID, "unknown ticket %d", ticket);
   DeviceGuard dg(h->device);
   CUDA_TRY(h, cudaEventSynchronize(it->second->ev_d2h[s]));
+  return IAN_OK;
+}
+
+// ---- sample_IAN.py function set (reference sample_IAN.py:86-94) ----------------------------------------
+// Zfn: X -> l_Z_IAF (deterministic: mu).  For IAN_simple there is no flow and this equals ian_encode_host.
+int ian_encode_pre_host(ian_handle* h, const float* x, int n, float* z_iaf) {
+  int rc = check_ready(h, n, x, z_iaf);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->x, x + (size_t)off * 12288, (size_t)cn * 12288 * 4, cudaMemcpyHostToDevice, st));
+    int r = run_encode(h, pl, pl->x, nullptr, pl->z, st, pl->eps /*staging for l_Z_IAF*/);
+    if (r != IAN_OK) return r;
+    CUDA_TRY(h, cudaMemcpyAsync(z_iaf + (size_t)off * 100, pl->eps, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// Z_IAF_fn: l_Z_IAF -> l_Z = (z - MADE_mu(z)) / exp(MADE_ls(z)); identity for IAN_simple.
+// x_out != NULL additionally decodes: `sample` of sample_IAN.py:86 (l_Z_IAF -> X).
+int ian_flow_host(ian_handle* h, const float* z_iaf, int n, float* z_out /*nullable*/, float* x_out /*nullable*/) {
+  int rc = check_ready(h, n, z_iaf, z_iaf);
+  if (rc != IAN_OK) return rc;
+  if (!z_out && !x_out) return fail(h, IAN_ERR_INVALID, "both outputs are NULL");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
+    CUDA_TRY(h, cudaMemcpyAsync(pl->eps, z_iaf + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
+    if (h->model_kind == IAN_MODEL_FULL)
+      LAUNCH_TRY(h, launch_made_iaf(pl->eps, h->made_w, h->made_b, pl->z, pl->zp.p, pl->zp.plane, cn, st));
+    else {
+      CUDA_TRY(h, cudaMemcpyAsync(pl->z, pl->eps, (size_t)cn * 400, cudaMemcpyDeviceToDevice, st));
+      LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
+    }
+    if (z_out) CUDA_TRY(h, cudaMemcpyAsync(z_out + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
+    if (x_out) {
+      int r = run_decode_from_planes(h, pl, pl->xhat, st);
+      if (r != IAN_OK) return r;
+      CUDA_TRY(h, cudaMemcpyAsync(x_out + (size_t)off * 12288, pl->xhat, (size_t)cn * 12288 * 4, cudaMemcpyDeviceToHost, st));
+    }
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(st));
   return IAN_OK;
 }
 

@@ -73,11 +73,20 @@ struct TapGemm {
   long long res_plane;
   __nv_bfloat16* out_raw;
   long long out_raw_plane;
-  // channel-major float32 output [n][cout_real][Hout*Wout] (columns >= cout_real are dropped): coalesced when a
-  // warp's 32 rows are consecutive pixels; used for the RGB-Beta head's tap table
+  // tile-blocked channel-major float32 output [m-tile][cout_real][128 rows] (columns >= cout_real dropped): every
+  // 128-row tile owns one contiguous block and a warp writes 128 contiguous bytes per column.  Row order inside a
+  // tile and tile order follow tile_shape() below.  Used for the RGB-Beta head's tap table.
   float* out_f32_t;
   int cout_real;
+  int passes;                   // 3 = float32 via bf16 hi|lo split (default), 1 = plain bf16 (hi planes only)
 };
+
+// 128-row M tiles are boxes {Nt images, Ht rows, Wt cols} of the (n, p, q) output grid
+__host__ __device__ inline void tile_shape(int Hg, int Wg, int& Wt, int& Ht, int& Nt) {
+  Wt = Wg < 128 ? Wg : 128;
+  Ht = Hg < 128 / Wt ? Hg : 128 / Wt;
+  Nt = 128 / (Wt * Ht);
+}
 
 __device__ __forceinline__ float act_apply(float v, int act) {
   switch (act) {

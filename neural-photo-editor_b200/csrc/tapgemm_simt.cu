@@ -10,10 +10,10 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;   // Cout may be 16 (RGB-Beta head): columns >= Cout are masked
 
-__device__ __forceinline__ float4 load_join4(const __nv_bfloat16* hi, long long plane) {
-  // 4 consecutive channels: hi and lo planes, 8 bytes each
+__device__ __forceinline__ float4 load_join4(const __nv_bfloat16* hi, long long plane, bool use_lo) {
+  // 4 consecutive channels: hi and lo planes, 8 bytes each (lo ignored in single-pass bf16 mode)
   uint2 h = *reinterpret_cast<const uint2*>(hi);
-  uint2 l = *reinterpret_cast<const uint2*>(hi + plane);
+  uint2 l = use_lo ? *reinterpret_cast<const uint2*>(hi + plane) : make_uint2(0u, 0u);
   const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
   const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
   float2 h0 = __bfloat1622float2(hp[0]), h1 = __bfloat1622float2(hp[1]);
@@ -31,9 +31,9 @@ __device__ __forceinline__ void epilogue_store(const TapGemm& g, float acc, long
     __nv_bfloat16 rh, rl;
     split_bf16(acc, rh, rl);
     g.out_raw[pix * g.Cout + co] = rh;
-    g.out_raw[g.out_raw_plane + pix * g.Cout + co] = rl;
+    if (g.passes != 1) g.out_raw[g.out_raw_plane + pix * g.Cout + co] = rl;
   }
-  if (g.res) acc += __bfloat162float(g.res[pix * g.Cout + co]) + __bfloat162float(g.res[g.res_plane + pix * g.Cout + co]);
+  if (g.res) acc += __bfloat162float(g.res[pix * g.Cout + co]) + (g.passes != 1 ? __bfloat162float(g.res[g.res_plane + pix * g.Cout + co]) : 0.f);
   if (g.act == ACT_MASK) {
     float mk = __bfloat162float(g.mask[pix * g.Cout + co]);
     v = mk > 0.f ? acc * sc : 0.f;
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
     const __nv_bfloat16* brow =
         g.b + ((long long)tap.wtile * g.Cout + (n0 + lr)) * g.Cin + lc;
     for (int c0 = 0; c0 < g.Cin; c0 += BK) {
-      float4 av = ok ? load_join4(arow + c0, g.a_plane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 bv = (n0 + lr < g.Cout) ? load_join4(brow + c0, g.b_plane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 av = ok ? load_join4(arow + c0, g.a_plane, g.passes != 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 bv = (n0 + lr < g.Cout) ? load_join4(brow + c0, g.b_plane, g.passes != 1) : make_float4(0.f, 0.f, 0.f, 0.f);
       __syncthreads();
       As[lc + 0][lr] = av.x; As[lc + 1][lr] = av.y; As[lc + 2][lr] = av.z; As[lc + 3][lr] = av.w;
       Bs[lc + 0][lr] = bv.x; Bs[lc + 1][lr] = bv.y; Bs[lc + 2][lr] = bv.z; Bs[lc + 3][lr] = bv.w;
@@ -121,14 +121,18 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
     for (int j = 0; j < 4; ++j) epilogue_store(g, acc[i][j], pix, oh, ow, co + j, hi4, lo4, f4, j);
     if (g.out) {
       *reinterpret_cast<uint2*>(g.out + pix * g.Cout + co) = *reinterpret_cast<uint2*>(hi4);
-      *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
+      if (g.passes != 1) *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
     }
     if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co) = *reinterpret_cast<float4*>(f4);
-    if (g.out_f32_t) {
-      const long long hw = (long long)g.Hout * g.Wout;
+    if (g.out_f32_t) {                                     // same tile-blocked layout as the tensor-core kernel
+      int Wt, Ht, Nt;
+      tile_shape(g.Hg, g.Wg, Wt, Ht, Nt);
+      const int tq = g.Wg / Wt, tp = g.Hg / Ht;
+      const long long mtile = ((long long)(n / Nt) * tp + p / Ht) * tq + q / Wt;
+      const int ml = ((n % Nt) * Ht + p % Ht) * Wt + q % Wt;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (co + j < g.cout_real) g.out_f32_t[((long long)n * g.cout_real + co + j) * hw + (long long)oh * g.Wout + ow] = f4[j];
+        if (co + j < g.cout_real) g.out_f32_t[(mtile * g.cout_real + co + j) * 128 + ml] = f4[j];
     }
   }
 }

@@ -27,8 +27,10 @@
 namespace ian {
 
 struct TcMaps {
-  CUtensorMap a[4];
-  CUtensorMap b;
+  CUtensorMap a[4];     // activation views, box = {64 ch, Wt, Ht, Nt, 2 planes}   (3-pass float32-split mode)
+  CUtensorMap b;        // weights, box = {64 ch, BN, 2 planes}
+  CUtensorMap a1[4];    // same tensors, hi plane only (single-pass bf16 mode)
+  CUtensorMap b1;
   int Wt, Ht, Nt, BN;
 };
 
@@ -39,19 +41,22 @@ using namespace tc;
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 320;                         // producer, MMA, 8 epilogue warps
-constexpr int kATileBytes = BM * BK * 2 * 2;            // hi + lo planes: 32 KB
 
 constexpr int kEpiWarps = 8;
 
-template <int BN> struct TcCfg {
-  static constexpr int kBTileBytes = BN * BK * 2 * 2;  // hi + lo
+// PASSES = 3: float32 fidelity, operands are bf16 hi|lo planes, 3 MMAs per K slice, main|cross accumulators.
+// PASSES = 1: plain bf16 (BASELINE configs[2]): hi planes only, 1 MMA per K slice, one accumulator.
+template <int BN, int PASSES> struct TcCfg {
+  static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
+  static constexpr int kATileBytes = BM * BK * 2 * kPlanes;
+  static constexpr int kBTileBytes = BN * BK * 2 * kPlanes;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStagesFit = (196 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kAccCols = 2 * BN;                      // TMEM columns of one buffer: main | cross
+  static constexpr int kAccCols = (PASSES == 3 ? 2 : 1) * BN;  // TMEM columns of one buffer: main | cross
   static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (kAccBufs * kAccCols <= 32) ? 32 : (kAccBufs * kAccCols <= 64) ? 64 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 1024;
 };
 
 template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { return tc::make_idesc_bf16_m128(BN); }
@@ -63,11 +68,11 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { r
 // of the current tile drains TMEM, and (when two accumulator buffers fit in the 512 TMEM columns) the
 // MMA warp starts the next tile while the epilogue warps are still converting/storing the previous one.
 struct WorkItem {
-  int phase, ks, n0, p0, q0, co0, it0, it1;
+  int phase, ks, n0, p0, q0, co0, it0, it1, mtile;
 };
 
-// CH float32 values -> bf16 hi|lo planes, 16-byte stores
-template <int CH>
+// CH float32 values -> bf16 hi|lo planes (hi only in single-pass mode), 16-byte stores
+template <int CH, int PASSES>
 __device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane, const float (&v)[CH]) {
   __align__(16) __nv_bfloat16 hi[CH], lo[CH];
 #pragma unroll
@@ -77,7 +82,7 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane,
 #pragma unroll
   for (int j = 0; j < CH / 8; ++j) {
     oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
-    ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+    if (PASSES == 3) ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
   }
 }
 
@@ -91,6 +96,7 @@ __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& 
   wi.phase = w / per_phase;
   int r = w % per_phase;
   int mt = r % tiles_m; r /= tiles_m;
+  wi.mtile = mt;
   const int nt = r % tiles_n; r /= tiles_n;
   wi.ks = r;
   const int qb = mt % tiles_q; mt /= tiles_q;
@@ -103,10 +109,11 @@ __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& 
   return wi;
 }
 
-template <int BN>
+template <int BN, int PASSES>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PASSES>;
+  constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -116,7 +123,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * S + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * S + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-  const uint32_t stage_smem = bar_base + 256u;       // per-epilogue-warp scale/shift staging: 8 x 64 floats
+  const uint32_t stage_smem = bar_base + 256u;       // per-epilogue-warp scale|shift staging: 8 x (128 + 128) floats
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_al + (tmem_slot - smem_base));
   float* stage_ptr = reinterpret_cast<float*>(smem_al + (stage_smem - smem_base));
@@ -156,8 +163,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           mbar_wait(empty_bar(s), par ^ 1u);
           mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          tma_load_5d(&maps.a[tap.view], full_bar(s), sa, c0, wi.q0 + tap.dw, wi.p0 + tap.dh, wi.n0, 0);
-          tma_load_3d(&maps.b, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
+          tma_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], full_bar(s), sa, c0, wi.q0 + tap.dw,
+                      wi.p0 + tap.dh, wi.n0, 0);
+          tma_load_3d(PASSES == 3 ? &maps.b : &maps.b1, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
         }
       }
     }
@@ -187,8 +195,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes per K=16 slice, in 16-byte units
             const uint32_t acc = (!first || k > 0) ? 1u : 0u;
             umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-            umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+            if (PASSES == 3) {
+              umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+              umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+            }
           }
           umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
         }
@@ -203,7 +213,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     const int lg = warp & 3;                            // TMEM lane group this warp may access
     const int half = ew >> 2;                           // which half of the tile's columns
     const bool has_cols = (BN >= 64) || half == 0;
-    float* my_stage = stage_ptr + ew * 64;
+    float* my_stage = stage_ptr + ew * 256;             // [0,128): scale, [128,256): shift of this warp's columns
+    // activation as a branch-free a*t + b*|t| (none / LeakyRectify(0.2) / rectify; lasagne forms)
+    const float act_a = g.act == ACT_LRELU ? 0.6f : g.act == ACT_RELU ? 0.5f : 1.f;
+    const float act_b = g.act == ACT_LRELU ? 0.4f : g.act == ACT_RELU ? 0.5f : 0.f;
     const int ml = lg * 32 + lane;                      // tile row
     const int wl = ml % maps.Wt;
     const int hl = (ml / maps.Wt) % maps.Ht;
@@ -219,6 +232,15 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
       const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
       const uint32_t lane_addr = tmem_base + buf * Cfg::kAccCols + ((uint32_t)(lg * 32) << 16);
 
+      if (has_cols && g.scale_pix_stride == 0) {         // stage this tile's per-channel scale/shift while the MMAs run
+        __syncwarp();
+        const int cbase = wi.co0 + half * COLS_PER_WARP;
+        for (int c = lane; c < COLS_PER_WARP; c += 32) {
+          my_stage[c] = g.scale ? __ldg(g.scale + cbase + c) : 1.f;
+          my_stage[128 + c] = g.shift ? __ldg(g.shift + cbase + c) : 0.f;
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
       if (has_cols && wi.it1 > wi.it0) {
@@ -228,13 +250,19 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           const int co = wi.co0 + cb;
           float v[CH];
           __syncwarp();                                 // tcgen05.ld is .aligned: reconverge first
-          {
+          if (PASSES == 3) {
             uint32_t vm[CH], vc[CH];
             tmem_ld<CH>(lane_addr + cb, vm);
             tmem_ld<CH>(lane_addr + BN + cb, vc);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]) + __uint_as_float(vc[j]);
+          } else {
+            uint32_t vm[CH];
+            tmem_ld<CH>(lane_addr + cb, vm);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]);
           }
           if (cc + CH >= COLS_PER_WARP) {               // last TMEM read of this work item: release the buffer
             tc_fence_before();
@@ -249,28 +277,25 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             }
             continue;
           }
-          // per-channel scale/shift of this chunk: one coalesced load per warp, broadcast through smem
-          if (g.scale_pix_stride == 0) {
-            __syncwarp();
-            if (lane < CH) {
-              my_stage[lane] = g.scale ? __ldg(g.scale + co + lane) : 1.f;
-              my_stage[32 + lane] = g.shift ? __ldg(g.shift + co + lane) : 0.f;
-            }
-            __syncwarp();
-          }
           if (valid) {
             const long long off = pix * g.Cout + co;
-            if (g.out_raw) store_split<CH>(g.out_raw + off, g.out_raw_plane, v);   // pre-BN value (MDBLOCK residual input)
+            if (g.out_raw) store_split<CH, PASSES>(g.out_raw + off, g.out_raw_plane, v);   // pre-BN value (MDBLOCK residual input)
             if (g.res) {                                   // residual add before BatchNorm (MDBLOCK, layers.py:411-416)
               const uint4* rh = reinterpret_cast<const uint4*>(g.res + off);
               const uint4* rl = reinterpret_cast<const uint4*>(g.res + g.res_plane + off);
 #pragma unroll
               for (int j8 = 0; j8 < CH / 8; ++j8) {
-                const uint4 h4 = __ldg(rh + j8), l4 = __ldg(rl + j8);
+                const uint4 h4 = __ldg(rh + j8);
                 const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h4);
-                const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l4);
+                if (PASSES == 3) {
+                  const uint4 l4 = __ldg(rl + j8);
+                  const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l4);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
+                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]);
+                }
               }
             }
             if (g.act == ACT_MASK) {
@@ -282,28 +307,34 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
                 const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&m4);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float sc = g.scale_pix_stride ? __ldg(g.scale + si + j8 * 8 + j) : my_stage[j8 * 8 + j];
+                  const float sc = g.scale_pix_stride ? __ldg(g.scale + si + j8 * 8 + j) : my_stage[cc + j8 * 8 + j];
                   v[j8 * 8 + j] = __bfloat162float(mb[j]) > 0.f ? v[j8 * 8 + j] * sc : 0.f;
                 }
               }
             } else {
 #pragma unroll
               for (int j4 = 0; j4 < CH / 4; ++j4) {
-                const float4 sc = *reinterpret_cast<const float4*>(my_stage + 4 * j4);
-                const float4 sf = *reinterpret_cast<const float4*>(my_stage + 32 + 4 * j4);
-                v[4 * j4 + 0] = act_apply(fmaf(v[4 * j4 + 0], sc.x, sf.x), g.act);
-                v[4 * j4 + 1] = act_apply(fmaf(v[4 * j4 + 1], sc.y, sf.y), g.act);
-                v[4 * j4 + 2] = act_apply(fmaf(v[4 * j4 + 2], sc.z, sf.z), g.act);
-                v[4 * j4 + 3] = act_apply(fmaf(v[4 * j4 + 3], sc.w, sf.w), g.act);
+                const float4 sc = *reinterpret_cast<const float4*>(my_stage + cc + 4 * j4);
+                const float4 sf = *reinterpret_cast<const float4*>(my_stage + 128 + cc + 4 * j4);
+                v[4 * j4 + 0] = fmaf(v[4 * j4 + 0], sc.x, sf.x);
+                v[4 * j4 + 1] = fmaf(v[4 * j4 + 1], sc.y, sf.y);
+                v[4 * j4 + 2] = fmaf(v[4 * j4 + 2], sc.z, sf.z);
+                v[4 * j4 + 3] = fmaf(v[4 * j4 + 3], sc.w, sf.w);
+              }
+              if (g.act == ACT_ELU) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+              } else if (g.act != ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] = fmaf(act_b, fabsf(v[j]), act_a * v[j]);
               }
             }
-            if (g.out) store_split<CH>(g.out + off, g.out_plane, v);
-            if (g.out_f32_t) {                           // channel-major fp32: [n][co][Hout*Wout], lanes = consecutive pixels
-              const long long hw = (long long)g.Hout * g.Wout;
-              float* ot = g.out_f32_t + ((long long)n * g.cout_real + co) * hw + (long long)oh * g.Wout + ow;
+            if (g.out) store_split<CH, PASSES>(g.out + off, g.out_plane, v);
+            if (g.out_f32_t) {                           // tile-blocked channel-major fp32: [m-tile][co][128 rows]
+              float* ot = g.out_f32_t + ((long long)wi.mtile * g.cout_real + co) * BM + ml;
 #pragma unroll
               for (int j = 0; j < CH; ++j)
-                if (co + j < g.cout_real) ot[j * hw] = v[j];
+                if (co + j < g.cout_real) ot[j * BM] = v[j];   // a warp writes 128 contiguous bytes per column
             }
             if (g.out_f32) {
               float4* of = reinterpret_cast<float4*>(g.out_f32 + off);
@@ -333,9 +364,7 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
   if (g.Cin % 64 || (g.Cout % 128 && g.Cout != 16)) { snprintf(err, errlen, "tc path needs Cin%%64==0 and Cout%%128==0 or Cout==16 (got %d,%d)", g.Cin, g.Cout); return nullptr; }
   TcMaps* m = new TcMaps();
   memset(m, 0, sizeof(*m));
-  m->Wt = g.Wg < BM ? g.Wg : BM;
-  m->Ht = g.Hg < BM / m->Wt ? g.Hg : BM / m->Wt;
-  m->Nt = BM / (m->Wt * m->Ht);
+  tile_shape(g.Hg, g.Wg, m->Wt, m->Ht, m->Nt);
   m->BN = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
   if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
     snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
@@ -364,6 +393,10 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A view %d) failed: %d", v, (int)r); delete m; return nullptr; }
+    box[4] = 1;
+    r = enc(&m->a1[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A1 view %d) failed: %d", v, (int)r); delete m; return nullptr; }
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)g.Cin, (cuuint64_t)(max_tile + 1) * g.Cout, 2};
@@ -374,6 +407,10 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete m; return nullptr; }
+    box[2] = 1;
+    r = enc(&m->b1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)g.b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(B1) failed: %d", (int)r); delete m; return nullptr; }
   }
   return m;
 }
@@ -382,16 +419,16 @@ void tc_free_maps(TcMaps* m) { delete m; }
 
 int tc_tile_width(const TcMaps* maps) { return maps->BN; }
 
-template <int BN>
+template <int BN, int PASSES>
 static int launch_one(const TapGemm& g, const TcMaps* maps, int total_work, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PASSES>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
     attr_set = true;
   }
-  tapgemm_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  tapgemm_tc_kernel<BN, PASSES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -405,9 +442,14 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
   const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
   const int total_work = tiles_m * (g.Cout / maps->BN) * g.nphase * g.ksplit;
   const int grid = total_work < num_sms ? total_work : num_sms;
-  if (maps->BN == 256) return launch_one<256>(g, maps, total_work, grid, st);
-  if (maps->BN == 128) return launch_one<128>(g, maps, total_work, grid, st);
-  return launch_one<16>(g, maps, total_work, grid, st);
+  if (g.passes == 1) {
+    if (maps->BN == 256) return launch_one<256, 1>(g, maps, total_work, grid, st);
+    if (maps->BN == 128) return launch_one<128, 1>(g, maps, total_work, grid, st);
+    return launch_one<16, 1>(g, maps, total_work, grid, st);
+  }
+  if (maps->BN == 256) return launch_one<256, 3>(g, maps, total_work, grid, st);
+  if (maps->BN == 128) return launch_one<128, 3>(g, maps, total_work, grid, st);
+  return launch_one<16, 3>(g, maps, total_work, grid, st);
 }
 
 }  // namespace ian

@@ -87,3 +87,54 @@ def test_custom_ordering_changes_masks(npe, PF):
     assert _zclose(z, zr)
     with pytest.raises(npe.IanError):
         npe.IAN("IAN.py", True, weights=PF, made_ordering=np.zeros(100, np.int32))
+
+
+def test_sample_ian_function_set(full_model, gold, PF):
+    """sample / sampleZ / Zfn / Z_IAF_fn of reference sample_IAN.py:86-94."""
+    x = on.to_tanh(gold["images"].astype(np.float64)).astype(np.float32)
+    z0 = full_model.Zfn(x)
+    assert np.abs(z0 - gold["mu"]).max() <= 2e-4
+    z = full_model.Z_IAF_fn(gold["mu"].astype(np.float32))
+    assert _zclose(z, gold["z"])
+    xs = full_model.sample(gold["mu"].astype(np.float32))
+    assert np.abs(xs - gold["xhat"]).max() <= 3e-4
+    assert np.abs(full_model.sampleZ(gold["z_rand"]) - gold["xhat_rand"]).max() <= 2e-4
+    grid = full_model.sample_grid(np.concatenate([x, x, x], 0), n_samples=3, seed=5)
+    assert grid.shape == (3 + 3 * 9, 3, 64, 64) and np.isfinite(grid).all()
+    assert np.array_equal(grid[3], x[0]) and np.array_equal(grid[3 + 8], x[1])     # endpoints bracket the interpolants
+
+
+def test_simple_model_function_set_is_flowless(model, golden):
+    x = on.to_tanh(golden["images"][:2].astype(np.float64)).astype(np.float32)
+    assert np.abs(model.Zfn(x) - model.encode_images(x)).max() <= 2e-5
+    z = golden["z_rand"][:2]
+    assert np.array_equal(model.Z_IAF_fn(z), z)
+    assert np.abs(model.sample(z) - model.sample_at(z)).max() <= 2e-5
+
+
+def test_bf16_mode_tolerance_vs_oracle(full_model, gold):
+    """BASELINE configs[2]: full IAN in bf16 with an fp32 tolerance check.  Operands rounded to bf16 (8 significand
+    bits), fp32 accumulation.  Measured on [-1,1] images: max-abs 0.10 (the Beta ratio 2a/(a+b) is steep where both
+    sigmoids are small), mean-abs 3.1e-3.  Bounds stated here: max-abs 0.2, mean-abs 8e-3."""
+    x = on.to_tanh(gold["images"].astype(np.float64)).astype(np.float32)
+    try:
+        full_model.set_precision("bf16")
+        xh = full_model.sample_at(gold["z_rand"])
+        err = np.abs(xh - gold["xhat_rand"])
+        assert err.max() <= 0.2 and err.mean() <= 8e-3, (err.max(), err.mean())
+        z = full_model.encode_images(x)
+        assert (np.abs(z - gold["z"]) <= 6e-2 * (1.0 + np.abs(gold["z"]))).all()
+        # the fp32 verification path run on the same bf16-rounded operands agrees to about the same level (bf16 re-rounding of activations amplifies 1-ulp differences)
+        full_model.set_path("simt")
+        xs = full_model.sample_at(gold["z_rand"])
+        full_model.set_path("tc")
+        assert np.abs(xs - xh).max() <= 0.1 and np.abs(xs - xh).mean() <= 5e-3, (np.abs(xs - xh).max(), np.abs(xs - xh).mean())
+    finally:
+        full_model.set_precision("fp32")
+        full_model.set_path("tc")
+    assert np.abs(full_model.sample_at(gold["z_rand"]) - gold["xhat_rand"]).max() <= 2e-4   # back to float32
+
+
+def test_bf16_mode_is_full_model_only(model, npe):
+    with pytest.raises(npe.IanError):
+        model.set_precision("bf16")

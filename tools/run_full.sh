@@ -1,5 +1,5 @@
 #!/bin/bash
-(timeout 900 python -m pytest tests/test_gpu_full.py -x -q -m gpu 2>&1 | tail -8)
+(timeout 900 python -m pytest tests/test_gpu_full.py -x -q -m gpu 2>&1 | tail -30)
 timeout 300 python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-edit 2>&1 | tail -1 > gpurun_out/bench_full.json
 python - <<'PY'
 import json
