@@ -71,12 +71,18 @@ struct WorkItem {
   int phase, ks, n0, p0, q0, co0, it0, it1, mtile;
 };
 
-// CH float32 values -> bf16 hi|lo planes (hi only in single-pass mode), 16-byte stores
+// CH float32 values -> bf16 hi|lo planes (hi only in single-pass mode), packed bf16x2 conversions, 16-byte stores
 template <int CH, int PASSES>
 __device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane, const float (&v)[CH]) {
-  __align__(16) __nv_bfloat16 hi[CH], lo[CH];
+  __align__(16) __nv_bfloat162 hi[CH / 2], lo[CH / 2];
 #pragma unroll
-  for (int j = 0; j < CH; ++j) split_bf16(v[j], hi[j], lo[j]);
+  for (int j = 0; j < CH / 2; ++j) {
+    hi[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    if (PASSES == 3) {
+      const float2 hf = __bfloat1622float2(hi[j]);
+      lo[j] = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+  }
   uint4* oh4 = reinterpret_cast<uint4*>(dst);
   uint4* ol4 = reinterpret_cast<uint4*>(dst + plane);
 #pragma unroll
