@@ -46,14 +46,17 @@ constexpr int kEpiWarps = 8;
 
 // PASSES = 3: float32 fidelity, operands are bf16 hi|lo planes, 3 MMAs per K slice, main|cross accumulators.
 // PASSES = 1: plain bf16 (BASELINE configs[2]): hi planes only, 1 MMA per K slice, one accumulator.
-template <int BN, int PASSES> struct TcCfg {
+// MT = M tiles (128 pixels each) per work item sharing ONE weight tile: MT = 2 turns the Cout = 128 layers from
+// operand-feed-bound (64 KB of smem fill per 128x128x64 MMA block) into the 128x256-equivalent intensity.
+template <int BN, int PASSES, int MT> struct TcCfg {
   static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
   static constexpr int kATileBytes = BM * BK * 2 * kPlanes;
   static constexpr int kBTileBytes = BN * BK * 2 * kPlanes;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
   static constexpr int kStagesFit = (196 * 1024) / kStageBytes;
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-  static constexpr int kAccCols = (PASSES == 3 ? 2 : 1) * BN;  // TMEM columns of one buffer: main | cross
+  static constexpr int kTileCols = (PASSES == 3 ? 2 : 1) * BN; // TMEM columns of one tile's accumulators: main | cross
+  static constexpr int kAccCols = MT * kTileCols;              // ... of one buffer
   static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (kAccBufs * kAccCols <= 32) ? 32 : (kAccBufs * kAccCols <= 64) ? 64 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 1024;
@@ -68,7 +71,8 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { r
 // of the current tile drains TMEM, and (when two accumulator buffers fit in the 512 TMEM columns) the
 // MMA warp starts the next tile while the epilogue warps are still converting/storing the previous one.
 struct WorkItem {
-  int phase, ks, n0, p0, q0, co0, it0, it1, mtile;
+  int phase, ks, co0, it0, it1;
+  int n0[2], p0[2], q0[2], mtile[2];   // up to MT = 2 M tiles
 };
 
 // CH float32 values -> bf16 hi|lo planes (hi only in single-pass mode), packed bf16x2 conversions, 16-byte stores
@@ -92,22 +96,31 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane,
   }
 }
 
-template <int BN>
+template <int BN, int MT>
 __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& maps, int w) {
   WorkItem wi;
   const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
   const int tiles_m = tiles_q * tiles_p * ((g.n_img + maps.Nt - 1) / maps.Nt);
+  const int groups_m = (tiles_m + MT - 1) / MT;
   const int tiles_n = g.Cout / BN;
-  const int per_phase = tiles_m * tiles_n * g.ksplit;
+  const int per_phase = groups_m * tiles_n * g.ksplit;
   wi.phase = w / per_phase;
   int r = w % per_phase;
-  int mt = r % tiles_m; r /= tiles_m;
-  wi.mtile = mt;
+  const int mg = r % groups_m; r /= groups_m;
   const int nt = r % tiles_n; r /= tiles_n;
   wi.ks = r;
-  const int qb = mt % tiles_q; mt /= tiles_q;
-  const int pb = mt % tiles_p; mt /= tiles_p;
-  wi.n0 = mt * maps.Nt; wi.p0 = pb * maps.Ht; wi.q0 = qb * maps.Wt;
+#pragma unroll
+  for (int j = 0; j < MT; ++j) {
+    int mt = mg * MT + j;
+    wi.mtile[j] = mt;
+    if (mt >= tiles_m) {                                // odd tile count: phantom tile, fully out of range
+      wi.n0[j] = g.n_img; wi.p0[j] = 0; wi.q0[j] = 0;
+      continue;
+    }
+    const int qb = mt % tiles_q; mt /= tiles_q;
+    const int pb = mt % tiles_p; mt /= tiles_p;
+    wi.n0[j] = mt * maps.Nt; wi.p0[j] = pb * maps.Ht; wi.q0[j] = qb * maps.Wt;
+  }
   wi.co0 = nt * BN;
   const int total_it = g.phase[wi.phase].ntaps * (g.Cin / BK);
   wi.it0 = (int)((long long)total_it * wi.ks / g.ksplit);
@@ -115,10 +128,10 @@ __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& 
   return wi;
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
-  using Cfg = TcCfg<BN, PASSES>;
+  using Cfg = TcCfg<BN, PASSES, MT>;
   constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -159,7 +172,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     if (lane == 0) {
       uint32_t i = 0;                                   // running K-step counter across work items
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem wi = decode_work<BN>(g, maps, w);
+        const WorkItem wi = decode_work<BN, MT>(g, maps, w);
         const Phase ph = g.phase[wi.phase];
         for (int it = wi.it0; it < wi.it1; ++it, ++i) {
           const int s = i % S;
@@ -169,9 +182,11 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           mbar_wait(empty_bar(s), par ^ 1u);
           mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          tma_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], full_bar(s), sa, c0, wi.q0 + tap.dw,
-                      wi.p0 + tap.dh, wi.n0, 0);
-          tma_load_3d(PASSES == 3 ? &maps.b : &maps.b1, full_bar(s), sa + kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
+#pragma unroll
+          for (int j = 0; j < MT; ++j)
+            tma_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], full_bar(s), sa + j * kATileBytes, c0,
+                        wi.q0[j] + tap.dw, wi.p0[j] + tap.dh, wi.n0[j], 0);
+          tma_load_3d(PASSES == 3 ? &maps.b : &maps.b1, full_bar(s), sa + MT * kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
         }
       }
     }
@@ -181,10 +196,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
       constexpr uint32_t idesc = make_idesc<BN>();
       uint32_t i = 0, t = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
-        const WorkItem wi = decode_work<BN>(g, maps, w);
+        const WorkItem wi = decode_work<BN, MT>(g, maps, w);
         const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
-        const uint32_t acc_main = tmem_base + buf * Cfg::kAccCols;
-        const uint32_t acc_cross = acc_main + BN;
+        const uint32_t acc_base = tmem_base + buf * Cfg::kAccCols;
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained this buffer
         tc_fence_after();
         for (int it = wi.it0; it < wi.it1; ++it, ++i) {
@@ -193,17 +207,21 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           mbar_wait(full_bar(s), par);
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + BM * BK * 2);
-          const uint64_t b_hi = make_sw128_desc(sa + kATileBytes), b_lo = make_sw128_desc(sa + kATileBytes + BN * BK * 2);
+          const uint64_t b_hi = make_sw128_desc(sa + MT * kATileBytes), b_lo = make_sw128_desc(sa + MT * kATileBytes + BN * BK * 2);
           const bool first = (it == wi.it0);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);     // 32 bytes per K=16 slice, in 16-byte units
-            const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-            umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-            if (PASSES == 3) {
-              umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-              umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+          for (int j = 0; j < MT; ++j) {
+            const uint64_t a_hi = make_sw128_desc(sa + j * kATileBytes), a_lo = make_sw128_desc(sa + j * kATileBytes + BM * BK * 2);
+            const uint32_t acc_main = acc_base + j * Cfg::kTileCols, acc_cross = acc_main + BN;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 slice, in 16-byte units
+              const uint32_t acc = (!first || k > 0) ? 1u : 0u;
+              umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+              if (PASSES == 3) {
+                umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+                umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+              }
             }
           }
           umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
@@ -229,15 +247,9 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     const int nl = ml / (maps.Wt * maps.Ht);
     uint32_t t = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
-      const WorkItem wi = decode_work<BN>(g, maps, w);
+      const WorkItem wi = decode_work<BN, MT>(g, maps, w);
       const Phase ph = g.phase[wi.phase];
       const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
-      const int n = wi.n0 + nl, p = wi.p0 + hl, q = wi.q0 + wl;
-      const bool valid = n < g.n_img;
-      const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
-      const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
-      const uint32_t lane_addr = tmem_base + buf * Cfg::kAccCols + ((uint32_t)(lg * 32) << 16);
-
       if (has_cols && g.scale_pix_stride == 0) {         // stage this tile's per-channel scale/shift while the MMAs run
         __syncwarp();
         const int cbase = wi.co0 + half * COLS_PER_WARP;
@@ -250,6 +262,13 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
       if (has_cols && wi.it1 > wi.it0) {
+#pragma unroll 1
+       for (int tj = 0; tj < MT; ++tj) {
+        const int n = wi.n0[tj] + nl, p = wi.p0[tj] + hl, q = wi.q0[tj] + wl;
+        const bool valid = n < g.n_img;
+        const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
+        const long long pix = (long long)(n * g.Hout + oh) * g.Wout + ow;
+        const uint32_t lane_addr = tmem_base + buf * Cfg::kAccCols + tj * Cfg::kTileCols + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
         for (int cc = 0; cc < COLS_PER_WARP; cc += CH) {
           const int cb = half * COLS_PER_WARP + cc;
@@ -270,7 +289,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(vm[j]);
           }
-          if (cc + CH >= COLS_PER_WARP) {               // last TMEM read of this work item: release the buffer
+          if (tj == MT - 1 && cc + CH >= COLS_PER_WARP) { // last TMEM read of this work item: release the buffer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -337,7 +356,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             }
             if (g.out) store_split<CH, PASSES>(g.out + off, g.out_plane, v);
             if (g.out_f32_t) {                           // tile-blocked channel-major fp32: [m-tile][co][128 rows]
-              float* ot = g.out_f32_t + ((long long)wi.mtile * g.cout_real + co) * BM + ml;
+              float* ot = g.out_f32_t + ((long long)wi.mtile[tj] * g.cout_real + co) * BM + ml;
 #pragma unroll
               for (int j = 0; j < CH; ++j)
                 if (co + j < g.cout_real) ot[j * BM] = v[j];   // a warp writes 128 contiguous bytes per column
@@ -349,6 +368,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             }
           }
         }
+       }
       } else {
         tc_fence_before();
         __syncwarp();
@@ -425,16 +445,18 @@ void tc_free_maps(TcMaps* m) { delete m; }
 
 int tc_tile_width(const TcMaps* maps) { return maps->BN; }
 
-template <int BN, int PASSES>
-static int launch_one(const TapGemm& g, const TcMaps* maps, int total_work, int grid, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PASSES>;
+template <int BN, int PASSES, int MT>
+static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN, PASSES, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
     attr_set = true;
   }
-  tapgemm_tc_kernel<BN, PASSES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  const int total_work = ((tiles_m + MT - 1) / MT) * (g.Cout / maps->BN) * g.nphase * g.ksplit;
+  const int grid = total_work < num_sms ? total_work : num_sms;
+  tapgemm_tc_kernel<BN, PASSES, MT><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -446,16 +468,19 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
-  const int total_work = tiles_m * (g.Cout / maps->BN) * g.nphase * g.ksplit;
-  const int grid = total_work < num_sms ? total_work : num_sms;
+  // Cout = 128 layers in bf16 mode: pair M tiles on one weight tile (halves the weight refills of these
+  // operand-feed-bound layers) once there is enough work to keep every SM busy.  In float32 mode the pair would need
+  // all 512 TMEM columns and lose the epilogue overlap -- measured slower, so it keeps single tiles.
+  const bool pair = maps->BN == 128 && g.passes == 1 && g.ksplit == 1 &&
+                    (long long)tiles_m * (g.Cout / 128) * g.nphase >= 2LL * num_sms;
   if (g.passes == 1) {
-    if (maps->BN == 256) return launch_one<256, 1>(g, maps, total_work, grid, st);
-    if (maps->BN == 128) return launch_one<128, 1>(g, maps, total_work, grid, st);
-    return launch_one<16, 1>(g, maps, total_work, grid, st);
+    if (maps->BN == 256) return launch_one<256, 1, 1>(g, maps, tiles_m, num_sms, st);
+    if (maps->BN == 128) return pair ? launch_one<128, 1, 2>(g, maps, tiles_m, num_sms, st) : launch_one<128, 1, 1>(g, maps, tiles_m, num_sms, st);
+    return launch_one<16, 1, 1>(g, maps, tiles_m, num_sms, st);
   }
-  if (maps->BN == 256) return launch_one<256, 3>(g, maps, total_work, grid, st);
-  if (maps->BN == 128) return launch_one<128, 3>(g, maps, total_work, grid, st);
-  return launch_one<16, 3>(g, maps, total_work, grid, st);
+  if (maps->BN == 256) return launch_one<256, 3, 1>(g, maps, tiles_m, num_sms, st);
+  if (maps->BN == 128) return launch_one<128, 3, 1>(g, maps, tiles_m, num_sms, st);
+  return launch_one<16, 3, 1>(g, maps, tiles_m, num_sms, st);
 }
 
 }  // namespace ian
