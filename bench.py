@@ -344,6 +344,20 @@ def main():
                 "unit": "sample-steps/sec", "loop_iters_per_sec": EDIT_STEPS / (ems / 1e3), "ms_total": ems,
                 "tflops": 2.5625 * EDIT_BATCH * EDIT_STEPS / (ems / 1e3) / 1e3}
 
+    # ---- BASELINE configs[0] size: one image, encode -> decode, through the synchronous host API (NPE's call pattern)
+    lat = None
+    if rank == 0:
+        x1 = x_np[:1].copy()
+        for _ in range(5):
+            model.reconstruct(x1)
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            model.reconstruct(x1)
+            ts.append(time.perf_counter() - t0)
+        lat = {"batch": 1, "median_ms": 1e3 * float(np.median(ts)), "min_ms": 1e3 * float(np.min(ts)),
+               "api": "IAN.reconstruct(numpy (1,3,64,64)), synchronous, includes H2D/D2H"}
+
     # ---- secondary block: full IAN (reference IAN.py graph), BASELINE configs[2] size (batch 512)
     full = None
     if not args.no_full and rank == 0:
@@ -397,7 +411,8 @@ def main():
                            "l2": "no flush: one step streams 211 MB of weights + ~1 GB of activations (> 126 MB L2)",
                            "collective": "all_gather of decoded images" if world > 1 else "none"},
                 "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": launches, "clocks": sampler.summary(), "edit": edit, "full_ian": full}
+                "gpu_launches": launches, "clocks": sampler.summary(), "edit": edit, "full_ian": full,
+                "single_image_latency": lat}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

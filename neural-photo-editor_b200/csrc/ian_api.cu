@@ -343,6 +343,29 @@ int choose_ksplit(const TapGemm& g) {
   return ks;
 }
 
+// Small batches (NPE runs batch 1): a layer with fewer tiles than SMs would stream its weights through a handful of
+// SMs.  Give every such layer the plan's shared split-K workspace so choose_ksplit() can spread K over the chip.
+int assign_splitk_workspace(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
+  long long need = 0;
+  std::vector<int> small;
+  for (int l : layers) {
+    TapGemm& g = pl->g[l];
+    if (g.out_f32_t) continue;
+    const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
+    const long long tiles = (long long)((g.n_img * g.Hg * g.Wg + 127) / 128) * (g.Cout / bn) * g.nphase;
+    if (tiles > 74) continue;
+    small.push_back(l);
+    const long long sz = (long long)g.n_img * g.Hout * g.Wout * g.Cout;
+    if (sz > need) need = sz;
+  }
+  if (small.empty()) return IAN_OK;
+  float* ws = nullptr;
+  int rc = alloc_buf(h, pl, ws, need);
+  if (rc != IAN_OK) return rc;
+  for (int l : small) pl->g[l].ws = ws;
+  return IAN_OK;
+}
+
 int finish_maps(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
   for (int l : layers) {
     char err[256] = {0};
@@ -386,7 +409,10 @@ int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
   // times), written channel-major; the dilated taps are applied afterwards as coalesced shifted reads (head_gather)
   set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
   g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
-  int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
+  int rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A,
+                                           F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4});
+  if (rc != IAN_OK) return rc;
+  rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
                                F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD});
   if (rc != IAN_OK) return rc;
   *out = pl;
@@ -454,6 +480,9 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
   g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
 
+  if ((rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
+                                            L_DEC_CONV2, L_DEC_CONV3, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1})) != IAN_OK)
+    return rc;
   for (int l = 0; l < F_DEC_FC2; ++l) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));

@@ -7,5 +7,6 @@ python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/bench_last.json').read())
 print("ms/step %.3f  img/s %.0f  e2e %.0f  edit %s" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["edit"] and round(d["edit"]["value"])), d["roofline"]["layer_ms"], d["roofline"]["edge_kernel_ms"], "frac %.3f" % d["roofline"]["frac"], "launches", d["gpu_launches"], d["clocks"])
-print("full_ian:", d.get("full_ian"))
+f = d.get("full_ian") or {}
+print("full_ian bf16 %.0f img/s, fp32 %.0f img/s" % (f.get("value", 0), (f.get("fp32_split") or {}).get("value", 0)), "| latency b1:", d.get("single_image_latency"))
 PY
