@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-edit", action="store_true")
     ap.add_argument("--no-full", action="store_true", help="skip the full-IAN (BASELINE configs[2]) block")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: all-gather fused into the dec_out kernel (peer stores over NVLink) or a separate NCCL all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -230,7 +232,31 @@ def main():
     assert stream != 0
     torch.cuda.synchronize()
 
+    gather_mode, gather_check = "none", None
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "p2p":
+            try:
+                model.setup_fused_gather(BATCH)
+                # one untimed cross-check of the fused gather against NCCL's all_gather
+                ptr = model.reconstruct_gather_dev(x.data_ptr(), BATCH, z.data_ptr(), stream)
+                model.reconstruct_dev(x.data_ptr(), BATCH, z.data_ptr(), xhat.data_ptr(), stream)
+                dist.all_gather_into_tensor(gathered, xhat)
+                torch.cuda.synchronize()
+                n_el = world * BATCH * 12288
+                # wrap the library's device buffer without copying
+                class _Ptr:                                   # __cuda_array_interface__ shim
+                    __cuda_array_interface__ = {"shape": (n_el,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+                fused = torch.as_tensor(_Ptr(), device=dev)
+                gather_check = float((fused - gathered.reshape(-1)).abs().max().item())
+            except Exception as e:                          # e.g. CUDA IPC not permitted in this container
+                gather_mode = "nccl"
+                gather_check = "p2p setup failed: %s" % (str(e)[:120],)
+
     def step():
+        if gather_mode == "p2p":
+            model.reconstruct_gather_dev(x.data_ptr(), BATCH, z.data_ptr(), stream)   # decode straight into every rank
+            return
         model.reconstruct_dev(x.data_ptr(), BATCH, z.data_ptr(), xhat.data_ptr(), stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, xhat)     # the one collective of the path (north_star)
@@ -409,7 +435,10 @@ def main():
                 "config": {"workload": "IAN_simple encode->decode, batch 256 per GPU (BASELINE configs[1])",
                            "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                            "l2": "no flush: one step streams 211 MB of weights + ~1 GB of activations (> 126 MB L2)",
-                           "collective": "all_gather of decoded images" if world > 1 else "none"},
+                           "collective": {"none": "none", "nccl": "NCCL all_gather of decoded images after dec_out",
+                                          "p2p": "all-gather fused into dec_out: st.global to every rank's buffer over NVLink "
+                                                 "peer memory + flag barrier"}[gather_mode],
+                           "gather_check_max_abs_vs_nccl": gather_check},
                 "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": sampler.summary(), "edit": edit, "full_ian": full,
                 "single_image_latency": lat}

@@ -113,6 +113,22 @@ int ian_reconstruct_wait(ian_handle* h, int ticket);
 int ian_host_alloc(ian_handle* h, size_t bytes, void** out);
 int ian_host_free(ian_handle* h, void* p);
 
+/* ---- data-parallel encode -> decode with the all-gather FUSED into the decoder's last kernel (no reference
+ * equivalent: the reference is single-GPU).  One process per GPU; every rank calls, in order:
+ *   ian_gather_create(h, world, rank, n_local, handle64)   allocate this rank's double gather buffer, get its 64-byte
+ *                                                          CUDA IPC handle
+ *   (exchange the handles between ranks with any transport, e.g. torch.distributed.all_gather)
+ *   ian_gather_connect(h, all_handles)                     map every peer's buffer (NVLink peer access)
+ *   ian_reconstruct_gather_dev(h, x, n_local, z, &gathered, stream)   per step
+ * The dec_out kernel stores each decoded image straight into slot `rank` of EVERY rank's gather buffer (st.global on
+ * peer pointers), then a flag barrier over peer memory makes the step complete: `gathered` (world*n_local,3,64,64)
+ * holds all ranks' images on return of the stream work.  Buffers alternate between steps; a result stays valid until
+ * the call after next. */
+int ian_gather_create(ian_handle* h, int world, int rank, int n_local, void* ipc_handle_out /*64 bytes*/);
+int ian_gather_connect(ian_handle* h, const void* all_handles /*world x 64 bytes*/);
+int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out /*nullable*/, float** gathered_out,
+                               void* stream);
+
 /* ---- the function set of the reference's sampling script (reference sample_IAN.py:86-94) ---------------------
  *   Zfn      : X -> l_Z_IAF (deterministic = mu, before the MADE/IAF flow)        -> ian_encode_pre_host
  *   Z_IAF_fn : l_Z_IAF -> l_Z = (z - MADE_mu(z)) / exp(MADE_ls(z))                 -> ian_flow_host(z_out)

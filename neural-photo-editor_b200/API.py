@@ -353,6 +353,32 @@ class IAN:
                                                  float(weight)))
         return z
 
+    # ---- multi-GPU: all-gather fused into the decoder's last kernel (peer stores over NVLink) ---------------------
+    def setup_fused_gather(self, n_local, group=None):
+        """Collective over `group` (torch.distributed, one process per GPU): allocate the gather buffers, exchange
+        their CUDA IPC handles and map the peers.  Afterwards reconstruct_gather_dev() decodes straight into every
+        rank's buffer."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = (C.c_ubyte * 64)()
+        self._check(self._lib.ian_gather_create(self._h, world, rank, int(n_local), C.cast(mine, C.c_void_p)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        local = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+        allh = torch.empty(world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, local, group=group)
+        blob = bytes(allh.cpu().tolist())
+        self._check(self._lib.ian_gather_connect(self._h, C.cast(C.create_string_buffer(blob, len(blob)), C.c_void_p)))
+        self._gather_world, self._gather_n = world, int(n_local)
+
+    def reconstruct_gather_dev(self, x_ptr, n_local, z_ptr=0, stream=0):
+        """encode -> decode of this rank's shard; returns the device pointer of the (world*n_local,3,64,64) float32
+        buffer that holds EVERY rank's decoded images once the stream work (incl. the peer barrier) has run."""
+        out = C.c_void_p()
+        self._check(self._lib.ian_reconstruct_gather_dev(self._h, x_ptr, int(n_local), z_ptr or None, C.byref(out),
+                                                         stream or None))
+        return out.value
+
     # ---- device-pointer variants (ints from torch.Tensor.data_ptr(); no host copies, async) ----------
     def reconstruct_dev(self, x_ptr, n, z_ptr, xhat_ptr, stream=0):
         self._check(self._lib.ian_reconstruct_dev(self._h, x_ptr, n, z_ptr or None, xhat_ptr, stream or None))

@@ -38,6 +38,9 @@ SIGNATURES = {
     "ian_reconstruct_wait": (C.c_int, [_H, C.c_int]),
     "ian_host_alloc": (C.c_int, [_H, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ian_host_free": (C.c_int, [_H, C.c_void_p]),
+    "ian_gather_create": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ian_gather_connect": (C.c_int, [_H, C.c_void_p]),
+    "ian_reconstruct_gather_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "ian_encode_pre_host": (C.c_int, [_H, _F, C.c_int, _F]),
     "ian_flow_host": (C.c_int, [_H, _F, C.c_int, _F, _F]),
     "ian_grad_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

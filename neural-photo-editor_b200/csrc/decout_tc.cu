@@ -22,9 +22,18 @@
 
 namespace ian {
 
+constexpr int kMaxPeers = 8;
+
 struct DecOutMaps {
   CUtensorMap a;   // h3 planes (C=128, W=32, H=32, N, 2)
   CUtensorMap b;   // weights  (C=128, 80 rows, 2)
+};
+
+// where the decoded images go: one buffer (single GPU) or the same offset of every rank's gather buffer -- the
+// all-gather of the data-parallel path is fused into this kernel's stores (peer pointers over NVLink)
+struct DecOutDst {
+  float* base[kMaxPeers];
+  int n;
 };
 
 namespace {
@@ -43,7 +52,7 @@ constexpr int kSmemBytes = 1024 + kAStages * kAStage + 2 * kBChunk + kTBytes + 2
 constexpr int kItemsPerImage = 16;           // 32 input rows / 2 interior rows per item
 
 __global__ void __launch_bounds__(kThreads, 1)
-decout_tc_kernel(const __grid_constant__ DecOutMaps maps, float* __restrict__ xhat, const int n_img) {
+decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant__ DecOutDst dst, const int n_img) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -174,10 +183,14 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, float* __restrict__ xh
           a0 += tp[0]; a1 += tp[1]; a2 += tp[2];
         }
       }
-      float* o = xhat + ((long long)n * 3 * 64 + (2 * p0 + ur)) * 64 + v;
-      o[0] = tanhf(a0);
-      o[4096] = tanhf(a1);
-      o[8192] = tanhf(a2);
+      const long long off = ((long long)n * 3 * 64 + (2 * p0 + ur)) * 64 + v;
+      const float y0 = tanhf(a0), y1 = tanhf(a1), y2 = tanhf(a2);
+      for (int d = 0; d < dst.n; ++d) {                  // d > 0: peer GPUs' gather buffers (st.global over NVLink)
+        float* o = dst.base[d] + off;
+        o[0] = y0;
+        o[4096] = y1;
+        o[8192] = y2;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");     // T tile consumed: may be overwritten
     }
   }
@@ -187,7 +200,38 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, float* __restrict__ xh
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- cross-GPU barrier over peer memory: every rank owns flags[kMaxPeers]; rank r writes its epoch into slot r of
+// every peer's array (release, system scope) and waits until all slots of its own array reached the epoch.
+__global__ void peer_signal_kernel(DecOutDst flags, int rank, int epoch) {
+  const int p = threadIdx.x;
+  if (p >= flags.n) return;
+  __threadfence_system();                                // order this GPU's earlier peer stores before the flag
+  int* slot = reinterpret_cast<int*>(flags.base[p]) + rank;
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(slot), "r"(epoch) : "memory");
+}
+
+__global__ void peer_wait_kernel(const int* my_flags, int world, int epoch) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  const long long t0 = clock64();
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(my_flags + p) : "memory");
+    if (clock64() - t0 > 20000000000LL) __trap();       // ~10 s: a peer died
+  } while (v < epoch);
+}
+
 }  // namespace
+
+int launch_peer_barrier(float* const* flag_ptrs, int world, int rank, int epoch, cudaStream_t st) {
+  if (world < 1 || world > kMaxPeers) return -1;
+  DecOutDst f;
+  f.n = world;
+  for (int d = 0; d < world; ++d) f.base[d] = flag_ptrs[d];
+  peer_signal_kernel<<<1, 32, 0, st>>>(f, rank, epoch);
+  peer_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const int*>(flag_ptrs[rank]), world, epoch);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
 
 DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,
                               long long wt_plane, char* err, int errlen) {
@@ -220,7 +264,7 @@ DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n
 
 void decout_free_maps(DecOutMaps* m) { delete m; }
 
-int launch_dec_out_tc(const DecOutMaps* maps, float* xhat, int n, cudaStream_t st) {
+int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int n, cudaStream_t st) {
   static bool attr_set = false;
   static int num_sms = 0;
   if (!attr_set) {
@@ -232,7 +276,11 @@ int launch_dec_out_tc(const DecOutMaps* maps, float* xhat, int n, cudaStream_t s
   }
   const int total = n * kItemsPerImage;
   const int grid = total < num_sms ? total : num_sms;
-  decout_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*maps, xhat, n);
+  if (ndst < 1 || ndst > kMaxPeers) return -1;
+  DecOutDst dst;
+  dst.n = ndst;
+  for (int d = 0; d < ndst; ++d) dst.base[d] = dsts[d];
+  decout_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*maps, dst, n);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

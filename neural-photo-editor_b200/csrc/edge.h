@@ -26,5 +26,8 @@ struct DecOutMaps;
 DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,
                               long long wt_plane, char* err, int errlen);
 void decout_free_maps(DecOutMaps*);
-int launch_dec_out_tc(const DecOutMaps* maps, float* xhat, int n, cudaStream_t st);
+// dsts[0..ndst): destination base pointers (1 = local only; >1 = every rank's gather buffer incl. peers)
+int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int n, cudaStream_t st);
+// signal + wait kernels of the peer-memory barrier (flag_ptrs[r] = rank r's flag array, int[8])
+int launch_peer_barrier(float* const* flag_ptrs, int world, int rank, int epoch, cudaStream_t st);
 }  // namespace ian

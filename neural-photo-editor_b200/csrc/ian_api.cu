@@ -151,6 +151,12 @@ struct ian_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined host API
   std::vector<void*> host_allocs;
+  // fused all-gather over NVLink peer memory (ian_gather_*): this rank's double gather buffer + flags, peers' views
+  int gw = 0, grank = 0, gn = 0, gcur = 0, gepoch = 0;
+  float* gbuf = nullptr;                       // [2][world][n_local][3][64][64] + flags (int[8]) at the end
+  float* gpeer_buf[8] = {nullptr};             // base of every rank's allocation (peer-mapped)
+  bool gconnected = false;
+  float** gather_dsts = nullptr;               // non-null only inside ian_reconstruct_gather_dev
   long long tickets = 0;
   std::string err;
   int64_t launches = 0;
@@ -597,8 +603,10 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
   ScopedTimer tm(h, T_DEC_OUT, st);
-  if (h->path == IAN_PATH_TC)
-    LAUNCH_TRY(h, launch_dec_out_tc(pl->decout_maps, xhat, pl->n, st));
+  if (h->path == IAN_PATH_TC) {
+    float* one[1] = {xhat};
+    LAUNCH_TRY(h, launch_dec_out_tc(pl->decout_maps, h->gather_dsts ? h->gather_dsts : one, h->gather_dsts ? h->gw : 1, pl->n, st));
+  }
   else
     LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
   return IAN_OK;
@@ -1077,6 +1085,8 @@ int ian_destroy(ian_handle* h) {
   cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (int r = 0; r < h->gw; ++r) if (r != h->grank && h->gpeer_buf[r]) cudaIpcCloseMemHandle(h->gpeer_buf[r]);
+  cudaFree(h->gbuf);
   for (void* p : h->host_allocs) cudaFreeHost(p);
   cudaStreamDestroy(h->stream);
   cudaStreamDestroy(h->h2d_stream);
@@ -1434,6 +1444,71 @@ int ian_flow_host(ian_handle* h, const float* z_iaf, int n, float* z_out /*nulla
   });
   if (rc != IAN_OK) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  return IAN_OK;
+}
+
+// ---- fused all-gather of decoded images over NVLink peer memory ---------------------------------------------
+static size_t gather_bytes(int world, int n_local) { return (size_t)2 * world * n_local * 12288 * sizeof(float) + 256; }
+
+int ian_gather_create(ian_handle* h, int world, int rank, int n_local, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(h, IAN_ERR_INVALID, "NULL argument");
+  if (!h->finalized) return fail(h, IAN_ERR_STATE, "ian_finalize() has not been called");
+  if (h->model_kind != IAN_MODEL_SIMPLE) return fail(h, IAN_ERR_UNSUPPORTED, "the fused gather is wired into the IAN_simple dec_out kernel");
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || n_local < 1 || n_local > h->max_chunk)
+    return fail(h, IAN_ERR_INVALID, "bad world/rank/n_local (%d,%d,%d)", world, rank, n_local);
+  if (h->gbuf) return fail(h, IAN_ERR_STATE, "gather buffers already created");
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaMalloc((void**)&h->gbuf, gather_bytes(world, n_local)));
+  CUDA_TRY(h, cudaMemset(h->gbuf, 0, gather_bytes(world, n_local)));
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&ipc, h->gbuf));
+  memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+  h->gw = world; h->grank = rank; h->gn = n_local;
+  return IAN_OK;
+}
+
+int ian_gather_connect(ian_handle* h, const void* all_handles) {
+  if (!h || !all_handles || !h->gbuf) return fail(h, IAN_ERR_STATE, "ian_gather_create() first");
+  DeviceGuard dg(h->device);
+  for (int r = 0; r < h->gw; ++r) {
+    if (r == h->grank) { h->gpeer_buf[r] = h->gbuf; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, (const char*)all_handles + (size_t)r * sizeof(ipc), sizeof(ipc));
+    void* p = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->gpeer_buf[r] = (float*)p;
+  }
+  h->gconnected = true;
+  return IAN_OK;
+}
+
+int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out, float** gathered_out, void* stream) {
+  int rc = check_ready(h, n_local, x, gathered_out);
+  if (rc != IAN_OK) return rc;
+  if (!h->gconnected) return fail(h, IAN_ERR_STATE, "ian_gather_connect() has not been called");
+  if (n_local != h->gn) return fail(h, IAN_ERR_INVALID, "n_local %d differs from the %d the gather buffers were sized for", n_local, h->gn);
+  if (h->path != IAN_PATH_TC) return fail(h, IAN_ERR_UNSUPPORTED, "fused gather runs on the tensor-core path");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  Plan* pl = nullptr;
+  if ((rc = get_plan(h, n_local, &pl)) != IAN_OK) return rc;
+  const size_t half = (size_t)h->gw * h->gn * 12288;             // floats per gather buffer
+  const size_t mine = (size_t)h->grank * h->gn * 12288;
+  float* dsts[8];
+  float* flags[8];
+  for (int r = 0; r < h->gw; ++r) {
+    dsts[r] = h->gpeer_buf[r] + (size_t)h->gcur * half + mine;    // my shard's slot in rank r's current buffer
+    flags[r] = h->gpeer_buf[r] + 2 * half;                        // rank r's flag array (int[8]) after its buffers
+  }
+  if ((rc = run_encode(h, pl, x, nullptr, z_out ? z_out : pl->z, st)) != IAN_OK) return rc;
+  h->gather_dsts = dsts;
+  rc = run_decode_from_planes(h, pl, nullptr, st);
+  h->gather_dsts = nullptr;
+  if (rc != IAN_OK) return rc;
+  h->gepoch += 1;
+  LAUNCH_TRY(h, launch_peer_barrier(flags, h->gw, h->grank, h->gepoch, st));
+  *gathered_out = h->gbuf + (size_t)h->gcur * half;
+  h->gcur ^= 1;
   return IAN_OK;
 }
 

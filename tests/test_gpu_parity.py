@@ -14,6 +14,8 @@ Tolerances (float32 path; stated per BASELINE north_star "within 1e-4 max-abs"):
                                       flip the same units.
   edited latents                    : max-abs <= 2e-2 * max move, median-abs <= 1e-4 * max move
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -173,6 +175,31 @@ def test_pipelined_stream_matches_sync(model):
     assert np.abs(out - want[0]).max() <= 2e-5 and np.abs(zo - model.encode_images(batches[0])).max() <= 2e-5
     with pytest.raises(TypeError):
         model.reconstruct(batches[0], out=np.empty((4, 3, 64, 64), np.float32))
+
+
+def test_fused_gather_world1(model):
+    """the dec_out -> gather-buffer path with a single rank (peer stores + flag barrier degenerate to local ones);
+    the 2-GPU form is cross-checked against NCCL inside bench.py (config.gather_check_max_abs_vs_nccl)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    rng = np.random.default_rng(21)
+    x = torch.from_numpy(rng.uniform(-1, 1, (6, 3, 64, 64)).astype(np.float32)).cuda()
+    z = torch.empty(6, 100, device="cuda")
+    model.setup_fused_gather(6)
+    want = model.reconstruct(x.cpu().numpy())
+    for _ in range(3):                                   # alternating buffers
+        ptr = model.reconstruct_gather_dev(x.data_ptr(), 6, z.data_ptr())
+        torch.cuda.synchronize()
+
+        class _Ptr:
+            __cuda_array_interface__ = {"shape": (6, 3, 64, 64), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        got = torch.as_tensor(_Ptr(), device="cuda").cpu().numpy()
+        assert np.abs(got - want).max() <= 2e-5
+    dist.destroy_process_group()
 
 
 def test_loader_rejects_bad_checkpoints(npe, weights):
