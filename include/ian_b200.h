@@ -158,6 +158,16 @@ int ian_edit_loop_dev(ian_handle* h, float* z, const int32_t* boxes, const float
 int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const float* target,
                        int target_is_frame, int n, int n_steps, float weight);
 
+/* ---- one NPE paint stroke in ONE call: replaces the body of paint() in photo mode (reference NPE.py:199-231):
+ *   g = imgradRGB(box, rgb_frame, z);  z <- z - weight * g * (1 + (c2 - c1));  x_hat = sample_at(z)
+ *   DELTA = x_hat - to_tanh(RECON);  MASK = gaussian_filter(min(mean_c|DELTA|, 1), 0.7)
+ *   IM = uint8(from_tanh(to_tanh(RECON) + MASK*DELTA + (1-MASK)*ERROR))
+ * z (1,100) in/out; box int32[4] = [c1,r1,c2,r2]; rgb_frame (1,3,64,64) float32 in [-1,1]; recon_u8 (3,64,64) uint8;
+ * error (3,64,64) float32; im_u8 (3,64,64) uint8 out; display_u8 (256,256,3) uint8 out (nullable): IM upsampled 4x
+ * nearest-neighbour in HWC order, what update_photo() hands to PIL (NPE.py:107-118).  IAN_MODEL_SIMPLE only. */
+int ian_paint_stroke_host(ian_handle* h, float* z, const int32_t* box, const float* rgb_frame, float weight,
+                          const uint8_t* recon_u8, const float* error, uint8_t* im_u8, uint8_t* display_u8);
+
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* Average device time (ms, CUDA events on the launch stream) of the tap-GEMM kernel of layer
  * `layer_name` ("enc_conv2", "dec_conv1", ...) over the launches since the last reset; returns <0 if

@@ -353,6 +353,28 @@ class IAN:
                                                  float(weight)))
         return z
 
+    def paint_stroke(self, z, box, rgb_frame, recon_u8, error, weight=0.05):
+        """One NPE paint stroke in photo mode in a single library call (reference NPE.py:199-231): brush gradient,
+        latent update, re-decode, DELTA/MASK(gaussian 0.7)/ERROR blend, uint8 conversion and the 4x display upsample.
+        z (1,100) float32; box = (x1,y1,x2,y2) as NPE computes it (integral floats accepted); rgb_frame (1,3,64,64)
+        float32 = to_tanh(myRGB); recon_u8 (3,64,64) uint8; error (3,64,64) float32.
+        Returns (z_new (1,100), IM uint8 (3,64,64), display uint8 (256,256,3) ready for PIL.Image.fromarray)."""
+        z = _f32(z, 2, 'z').copy()
+        frame = _f32(rgb_frame, 4, 'RGB')
+        if z.shape != (1, 100) or frame.shape != (1, 3, 64, 64):
+            raise TypeError("paint_stroke takes z (1,100) and RGB (1,3,64,64)")
+        bx = np.array([_int_scalar(v, n) for v, n in zip(box, ('x1', 'y1', 'x2', 'y2'))], np.int32)
+        recon = np.ascontiguousarray(recon_u8)
+        err = _f32(error, 3, 'error')
+        if recon.dtype != np.uint8 or recon.shape != (3, 64, 64) or err.shape != (3, 64, 64):
+            raise TypeError("recon_u8 must be uint8 (3,64,64) and error float32 (3,64,64)")
+        im = np.empty((3, 64, 64), np.uint8)
+        disp = np.empty((256, 256, 3), np.uint8)
+        self._check(self._lib.ian_paint_stroke_host(self._h, _fp(z), bx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(frame),
+                                                    float(weight), recon.ctypes.data_as(C.c_void_p), _fp(err),
+                                                    im.ctypes.data_as(C.c_void_p), disp.ctypes.data_as(C.c_void_p)))
+        return z, im, disp
+
     # ---- multi-GPU: all-gather fused into the decoder's last kernel (peer stores over NVLink) ---------------------
     def setup_fused_gather(self, n_local, group=None):
         """Collective over `group` (torch.distributed, one process per GPU): allocate the gather buffers, exchange

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ian_edit_loop_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_void_p]),
     "ian_edit_loop_host": (C.c_int, [_H, _F, _I, _F, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "ian_paint_stroke_host": (C.c_int, [_H, _F, _I, _F, C.c_float, C.c_void_p, _F, C.c_void_p, C.c_void_p]),
     "ian_set_layer_timing": (C.c_int, [_H, C.c_int]),
     "ian_layer_time_ms": (C.c_double, [_H, C.c_char_p, C.c_int]),
 }

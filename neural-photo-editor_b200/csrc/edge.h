@@ -15,6 +15,8 @@ int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* 
                           long long plane, int n, cudaStream_t st);
 int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
                         __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st);
+// NPE photo-mode blend + display upsample after a stroke (NPE.py:107-118, 218-231)
+int launch_npe_blend(const float* xhat, const uint8_t* recon, const float* error, uint8_t* im, uint8_t* display, cudaStream_t st);
 // full IAN: MADE+IAF latent flow and the autoregressive RGB-Beta head
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st);

@@ -413,6 +413,67 @@ __global__ void head_b_out_kernel(const float* __restrict__ ha, const float* __r
   o[8192] = 2.f * (B0 / (B0 + B1 + 1e-8f)) - 1.f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// NPE photo-mode blend after a paint stroke (reference NPE.py:218-231), one 64x64 image, one block:
+//   DELTA = x_hat - to_tanh(RECON);  M = min(mean_c |DELTA|, 1);  MASK = gaussian_filter(M, sigma=0.7)
+//   D = MASK*DELTA + (1-MASK)*ERROR;  IM = uint8(from_tanh(to_tanh(RECON) + D))
+// gaussian_filter = scipy.ndimage: separable, radius int(4*0.7+0.5) = 3, weights exp(-k^2/(2 sigma^2)) normalised,
+// boundary mode 'reflect' (d c b a | a b c d | d c b a), axis 0 then axis 1.
+// Also writes the 4x nearest-neighbour upsampled display image (NPE.py:107-118) as HWC uint8 (256,256,3).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect64(int i) { return i < 0 ? -i - 1 : (i > 63 ? 127 - i : i); }
+
+__global__ void __launch_bounds__(1024) npe_blend_kernel(const float* __restrict__ xhat, const uint8_t* __restrict__ recon,
+                                                         const float* __restrict__ error, uint8_t* __restrict__ im,
+                                                         uint8_t* __restrict__ display) {
+  __shared__ float M[64][65], T[64][65];
+  __shared__ float wk[4];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    float w[4], sum = 0.f;
+    for (int k = 0; k < 4; ++k) { w[k] = expf(-0.5f * (float)(k * k) / (0.7f * 0.7f)); sum += (k == 0 ? w[k] : 2.f * w[k]); }
+    for (int k = 0; k < 4; ++k) wk[k] = w[k] / sum;
+  }
+  for (int i = tid; i < 4096; i += 1024) {
+    float m = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float rt = 2.0f * ((float)recon[c * 4096 + i] / 255.0f) - 1.0f;       // to_tanh (NPE.py:37-38)
+      m += fabsf(xhat[c * 4096 + i] - rt);
+    }
+    M[i >> 6][i & 63] = fminf(m / 3.f, 1.f);
+  }
+  __syncthreads();
+  for (int i = tid; i < 4096; i += 1024) {                // axis 0 (rows)
+    const int r = i >> 6, c = i & 63;
+    float a = wk[0] * M[r][c];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) a += wk[k] * (M[reflect64(r - k)][c] + M[reflect64(r + k)][c]);
+    T[r][c] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < 4096; i += 1024) {                // axis 1 (columns) + blend
+    const int r = i >> 6, c = i & 63;
+    float mask = wk[0] * T[r][c];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) mask += wk[k] * (T[r][reflect64(c - k)] + T[r][reflect64(c + k)]);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float rt = 2.0f * ((float)recon[ch * 4096 + i] / 255.0f) - 1.0f;
+      const float delta = xhat[ch * 4096 + i] - rt;
+      const float d = mask * delta + (1.f - mask) * error[ch * 4096 + i];
+      float v = 255.0f * ((rt + d) + 1.f) / 2.0f;                                // from_tanh (NPE.py:40-41)
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      const uint8_t u = (uint8_t)v;                                              // np.uint8 truncates
+      im[ch * 4096 + i] = u;
+#pragma unroll
+      for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) display[((4 * r + dy) * 256 + 4 * c + dx) * 3 + ch] = u;
+    }
+  }
+}
+
 }  // namespace
 
 #define CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? 1 : -1)
@@ -464,6 +525,11 @@ int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, f
 }  // namespace ian
 
 namespace ian {
+int launch_npe_blend(const float* xhat, const uint8_t* recon, const float* error, uint8_t* im, uint8_t* display, cudaStream_t st) {
+  npe_blend_kernel<<<1, 1024, 0, st>>>(xhat, recon, error, im, display);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st) {
   made_iaf_kernel<<<n, 128, 0, st>>>(z0, mw, mb, z, zp, zplane, n);

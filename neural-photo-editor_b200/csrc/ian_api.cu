@@ -219,6 +219,7 @@ struct Plan {
   int32_t* boxes = nullptr;
   // full IAN activations (NHWC split planes): block input x, pre-activated t0, mid t2, block output y per scale
   Planes fh0, fx1, ft1, fu1, fy1, fx2, ft2, fu2, fy2, fx3, ft3, fu3, fy3, fh4;
+  uint8_t* stroke = nullptr;     // ian_paint_stroke_host staging (allocated on first use)
   float *z0 = nullptr, *ha = nullptr, *rg = nullptr, *tt = nullptr;   // tt: head tap table [n][198][4096]
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
@@ -1509,6 +1510,45 @@ int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float
   LAUNCH_TRY(h, launch_peer_barrier(flags, h->gw, h->grank, h->gepoch, st));
   *gathered_out = h->gbuf + (size_t)h->gcur * half;
   h->gcur ^= 1;
+  return IAN_OK;
+}
+
+// ---- one NPE paint stroke in one call (reference NPE.py:192-235, photo mode) ---------------------------------
+int ian_paint_stroke_host(ian_handle* h, float* z, const int32_t* box, const float* rgb_frame, float weight,
+                          const uint8_t* recon_u8, const float* error, uint8_t* im_u8, uint8_t* display_u8) {
+  int rc = check_ready(h, 1, z, rgb_frame);
+  if (rc != IAN_OK) return rc;
+  if ((rc = check_brush_supported(h)) != IAN_OK) return rc;
+  if (!box || !recon_u8 || !error || !im_u8) return fail(h, IAN_ERR_INVALID, "NULL argument");
+  if ((rc = validate_boxes(h, box, 1)) != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = h->stream;
+  Plan* pl = nullptr;
+  if ((rc = get_plan(h, 1, &pl)) != IAN_OK) return rc;
+  // staging buffer of the stroke: error (float32) | recon (u8) | IM (u8) | display (u8 HWC)
+  if (!pl->stroke) {
+    uint8_t* p = nullptr;
+    if ((rc = alloc_buf(h, pl, p, 49152 + 12288 + 12288 + 256 * 256 * 3)) != IAN_OK) return rc;
+    pl->stroke = p;
+  }
+  float* d_error = reinterpret_cast<float*>(pl->stroke);
+  uint8_t* d_recon = pl->stroke + 49152;
+  uint8_t* d_im = d_recon + 12288;
+  uint8_t* d_disp = d_im + 12288;
+  CUDA_TRY(h, cudaMemcpyAsync(pl->z, z, 400, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(pl->boxes, box, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(pl->target, rgb_frame, 12288 * 4, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(d_recon, recon_u8, 12288, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(d_error, error, 12288 * 4, cudaMemcpyHostToDevice, st));
+  LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, 1, st));
+  if ((rc = run_grad_core(h, pl, pl->boxes, pl->target, 1, st)) != IAN_OK) return rc;           // NPE.py:205
+  LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, 1, st));  // :206-209
+  if ((rc = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return rc;                   // NPE.py:218 sample_at
+  LAUNCH_TRY(h, launch_npe_blend(pl->xhat, d_recon, d_error, d_im, d_disp, st));                  // NPE.py:218-231
+  CUDA_TRY(h, cudaMemcpyAsync(z, pl->z, 400, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(im_u8, d_im, 12288, cudaMemcpyDeviceToHost, st));
+  if (display_u8) CUDA_TRY(h, cudaMemcpyAsync(display_u8, d_disp, 256 * 256 * 3, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
   return IAN_OK;
 }
 

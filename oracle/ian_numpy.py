@@ -290,3 +290,20 @@ def to_tanh(x):
 def from_tanh(x):
     """NPE.py:40-41."""
     return 255.0 * (x + 1) / 2.0
+
+
+def npe_paint_blend(xhat, recon_u8, error):
+    """The photo-mode blend of NPE.paint (NPE.py:218-231) for one decoded image xhat (3,64,64):
+    returns IM uint8 (3,64,64).  Uses scipy's gaussian_filter exactly as the reference does."""
+    import scipy.ndimage
+    recon_t = to_tanh(np.float32(recon_u8))                                   # NPE.py:218 to_tanh(np.float32(RECON))
+    DELTA = np.asarray(xhat, np.float32) - recon_t
+    MASK = scipy.ndimage.gaussian_filter(np.min([np.mean(np.abs(DELTA), axis=0), np.ones((64, 64))], axis=0), 0.7)
+    D = MASK * DELTA + (1 - MASK) * np.asarray(error)
+    return np.uint8(from_tanh(to_tanh(recon_u8) + D))                         # NPE.py:231
+
+
+def npe_display(im_u8):
+    """update_photo's 4x nearest upsample + HWC interleave (NPE.py:107-118)."""
+    data = np.repeat(np.repeat(np.uint8(im_u8), 4, 1), 4, 2)
+    return np.concatenate([data[c].reshape(256, 256, 1) for c in range(3)], axis=2)

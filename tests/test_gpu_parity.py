@@ -127,15 +127,17 @@ def test_tc_matches_simt(model):
 
 @pytest.mark.parametrize("n", [1, 3, 127, 130])
 def test_ragged_batches_and_sample_independence(model, n):
-    """inference BN keeps samples independent: any batch must equal its samples run alone."""
+    """inference BN keeps samples independent: any batch must equal its samples run alone -- up to summation order:
+    small batches split K across SMs (fp32 atomics), large ones do not, so the two differ like two float32
+    evaluations of the same sum (bounded by the oracle tolerances)."""
     rng = np.random.default_rng(n)
     x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
     xh, z = model.reconstruct(x, return_z=True)
     assert np.isfinite(xh).all() and np.isfinite(z).all()
     pick = sorted({0, n // 2, n - 1})
     xh1, z1 = model.reconstruct(x[pick], return_z=True)
-    assert np.abs(z[pick] - z1).max() <= 2e-5
-    assert np.abs(xh[pick] - xh1).max() <= 2e-5
+    assert np.abs(z[pick] - z1).max() <= Z_TOL
+    assert np.abs(xh[pick] - xh1).max() <= 5e-5
 
 
 def test_full_size_batch256_properties(model, weights):
@@ -175,6 +177,25 @@ def test_pipelined_stream_matches_sync(model):
     assert np.abs(out - want[0]).max() <= 2e-5 and np.abs(zo - model.encode_images(batches[0])).max() <= 2e-5
     with pytest.raises(TypeError):
         model.reconstruct(batches[0], out=np.empty((4, 3, 64, 64), np.float32))
+
+
+def test_paint_stroke_matches_npe_paint(model, golden, weights):
+    """one stroke = one call: gradient step, re-decode and NPE's DELTA/MASK/ERROR blend (NPE.py:199-231)."""
+    x = on.to_tanh(golden["images"][:1].astype(np.float64)).astype(np.float32)
+    z0 = model.encode_images(x)
+    recon = np.uint8(on.from_tanh(model.sample_at(z0)[0]))                       # NPE.py:261
+    error = (on.to_tanh(np.float32(golden["images"][0])) - on.to_tanh(np.float32(recon))).astype(np.float32)
+    box = [float(v) for v in golden["boxes"][1]]                                  # integral floats, like NPE.py:202
+    rgb = np.broadcast_to(golden["rgb"][1].reshape(1, 3, 1, 1), (1, 3, 64, 64)).astype(np.float32).copy()
+    z1, im, disp = model.paint_stroke(z0, box, rgb, recon, error, weight=0.05)
+    # reference sequence through the separate calls + the oracle's restatement of the blend
+    g = model.imgradRGB(box[0], box[1], box[2], box[3], rgb, z0)
+    z_ref = z0 - 0.05 * g * (1 + (box[2] - box[0]))
+    assert np.abs(z1 - z_ref).max() <= 1e-5 * max(1.0, np.abs(z_ref).max())
+    im_ref = on.npe_paint_blend(model.sample_at(z1.astype(np.float32))[0], recon, error)
+    assert np.abs(im.astype(np.int32) - im_ref.astype(np.int32)).max() <= 1          # uint8 truncation at a float edge
+    assert (im != im_ref).mean() <= 0.01
+    assert np.array_equal(disp, on.npe_display(im)) and disp.shape == (256, 256, 3)
 
 
 def test_fused_gather_world1(model):
