@@ -23,6 +23,12 @@ int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z,
 int launch_head_gather(const float* tt, const int* taps, int ntaps, float* ha, int n, cudaStream_t st);
 int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
                          float* xhat, int n, cudaStream_t st);
+// enc_conv1 on the tensor-core path (conv1_tc.cu): thread-built im2col tile + tcgen05
+struct Conv1Maps;
+Conv1Maps* conv1_build_maps(const __nv_bfloat16* wt, long long wt_plane, char* err, int errlen);
+void conv1_free_maps(Conv1Maps*);
+int launch_conv1_tc(const Conv1Maps* maps, const float* x, const float* bias, __nv_bfloat16* out, long long plane, int n,
+                    cudaStream_t st);
 // dec_out on the tensor-core path (decout_tc.cu)
 struct DecOutMaps;
 DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,

@@ -164,6 +164,8 @@ struct ian_handle {
   DevWeights w[L_COUNT];
   float* conv1_wt = nullptr;   // [75][128]
   float* conv1_b = nullptr;    // [128]
+  __nv_bfloat16* conv1_tc_wt = nullptr;    // [2][128 cout][128 k] bf16 planes, k = c*25+i*5+j (75 used)
+  Conv1Maps* conv1_maps = nullptr;
   float* decout_wt = nullptr;  // [25][128][4] fp32 (SIMT forward + brush backward)
   __nv_bfloat16* decout_tc_wt = nullptr;   // [2][80][128] bf16 planes, row = tap*3+co (tensor-core forward)
   // full IAN extras
@@ -575,7 +577,10 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
   const int n = pl->n;
   {
     ScopedTimer tm(h, T_CONV1, st);
-    LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+    if (h->path == IAN_PATH_TC)
+      LAUNCH_TRY(h, launch_conv1_tc(h->conv1_maps, x, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+    else
+      LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
   }
   int rc;
   for (int l : {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD})
@@ -751,6 +756,19 @@ int prepare_encoder(ian_handle* h) {
     const auto& b = P(h, "enc_conv1.b").data;
     CUDA_TRY(h, cudaMalloc((void**)&h->conv1_b, 128 * 4));
     CUDA_TRY(h, cudaMemcpy(h->conv1_b, b.data(), 128 * 4, cudaMemcpyHostToDevice));
+    // tensor-core form: B[co][k] = W[co][c][i][j] (the reference layout flattened), K padded 75 -> 128, hi|lo planes
+    std::vector<uint16_t> planes(2 * 128 * 128, 0);
+    for (int o = 0; o < 128; ++o)
+      for (int k = 0; k < 75; ++k) {
+        const uint16_t hi = f2bf(W[o * 75 + k]);
+        planes[o * 128 + k] = hi;
+        planes[128 * 128 + o * 128 + k] = f2bf(W[o * 75 + k] - bf2f(hi));
+      }
+    CUDA_TRY(h, cudaMalloc((void**)&h->conv1_tc_wt, planes.size() * 2));
+    CUDA_TRY(h, cudaMemcpy(h->conv1_tc_wt, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    char err[256] = {0};
+    h->conv1_maps = conv1_build_maps(h->conv1_tc_wt, 128 * 128, err, sizeof(err));
+    if (!h->conv1_maps) return fail(h, IAN_ERR_CUDA, "enc_conv1: %s", err);
   }
   return IAN_OK;
 }
@@ -1084,6 +1102,7 @@ int ian_destroy(ian_handle* h) {
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
   cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
+  cudaFree(h->conv1_tc_wt); if (h->conv1_maps) conv1_free_maps(h->conv1_maps);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (int r = 0; r < h->gw; ++r) if (r != h->grank && h->gpeer_buf[r]) cudaIpcCloseMemHandle(h->gpeer_buf[r]);
