@@ -187,22 +187,35 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
     const int pt = threadIdx.x - 320;                   // 0..255
     const int m = pt >> 1, hsel = pt & 1;
     const int r = m >> 5, c = m & 31;
+    // the patch of tile t+1 is fetched into registers while tile t is being expanded (global latency hidden)
+    constexpr int kPer = (kPatchFloats + kProducers - 1) / kProducers;    // 9 floats per thread
+    float pre[kPer];
+    auto fetch = [&](int w) {
+      const int n = w / kTilesPerImage, p0 = (w % kTilesPerImage) * 4;
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int i = pt + e * kProducers;
+        float v = 0.f;
+        if (i < kPatchFloats) {
+          const int ch = i / (kPatchRows * kPatchCols), rem = i % (kPatchRows * kPatchCols);
+          const int iy = 2 * p0 - 2 + rem / kPatchCols, ix = rem % kPatchCols - 2;   // rows 2*p0-2..2*p0+8, cols -2..65
+          if (iy >= 0 && iy < 64 && ix >= 0 && ix < 64) v = __ldg(x + (((long long)n * 3 + ch) * 64 + iy) * 64 + ix);
+        }
+        pre[e] = v;
+      }
+    };
+    if ((int)blockIdx.x < total) fetch(blockIdx.x);
     uint32_t t = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++t) {
-      const int n = w / kTilesPerImage, p0 = (w % kTilesPerImage) * 4;
       const uint32_t s = t & 1u, use = t >> 1;
       float* patch = reinterpret_cast<float*>(smem_al + (p_base - smem_base)) + s * kPatchFloats;
       uint8_t* stage = smem_al + (a_base - smem_base) + s * kAStage;
-      mbar_wait(empty_bar(s), (use & 1u) ^ 1u);         // the MMAs that read this stage (and patch) have retired
-      // input patch: rows 2*p0-2 .. 2*p0+8, cols -2 .. 65, zero padded
-      for (int i = pt; i < kPatchFloats; i += kProducers) {
-        const int ch = i / (kPatchRows * kPatchCols), rem = i % (kPatchRows * kPatchCols);
-        const int iy = 2 * p0 - 2 + rem / kPatchCols, ix = rem % kPatchCols - 2;
-        float v = 0.f;
-        if (iy >= 0 && iy < 64 && ix >= 0 && ix < 64) v = __ldg(x + (((long long)n * 3 + ch) * 64 + iy) * 64 + ix);
-        patch[i] = v;
-      }
+      mbar_wait(empty_bar(s), (use & 1u) ^ 1u);         // the MMAs that read this stage have retired
+#pragma unroll
+      for (int e = 0; e < kPer; ++e)
+        if (pt + e * kProducers < kPatchFloats) patch[pt + e * kProducers] = pre[e];
       asm volatile("bar.sync 2, 256;" ::: "memory");    // patch complete (producer warps only)
+      if (w + (int)gridDim.x < total) fetch(w + gridDim.x);
       if (hsel == 0) build_half<0>(stage, patch, m, r, c); else build_half<1>(stage, patch, m, r, c);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
       __syncwarp();
