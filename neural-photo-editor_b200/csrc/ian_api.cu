@@ -147,6 +147,10 @@ struct ian_handle {
   int model_kind = 0;
   int path = IAN_PATH_TC;
   int passes = 3;              // 3: float32 semantics (bf16 hi|lo split); 1: plain bf16 tensor-core math
+  float* sk_ws = nullptr;      // stream-K partial-sum slots + arrival flags (shared by all layers of the handle)
+  int* sk_flags = nullptr;
+  int sk_epoch = 0;
+  bool streamk = true;
   bool finalized = false;
   cudaStream_t stream = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined host API
@@ -549,6 +553,9 @@ struct ScopedTimer {
 int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
   g.passes = h->passes;
+  g.sk_ws = h->streamk ? h->sk_ws : nullptr;
+  g.sk_flags = h->sk_flags;
+  g.sk_epoch = ++h->sk_epoch;
   ian_handle::Timed tm{};
   if (h->timing) {
     CUDA_TRY(h, cudaEventCreate(&tm.e0));
@@ -1039,6 +1046,7 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   }
   if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
+  if (const char* c = getenv("IAN_STREAMK")) h->streamk = atoi(c) != 0;
   *out = h;
   return IAN_OK;
 }
@@ -1088,6 +1096,9 @@ int ian_finalize(ian_handle* h) {
   if (rc != IAN_OK) return rc;
   rc = h->model_kind == IAN_MODEL_FULL ? prepare_full_decoder(h) : prepare_simple_decoder(h);
   if (rc != IAN_OK) return rc;
+  CUDA_TRY(h, cudaMalloc((void**)&h->sk_ws, tc_sk_workspace_floats() * sizeof(float)));
+  CUDA_TRY(h, cudaMalloc((void**)&h->sk_flags, tc_sk_flag_ints() * sizeof(int)));
+  CUDA_TRY(h, cudaMemset(h->sk_flags, 0, tc_sk_flag_ints() * sizeof(int)));
   h->params.clear();
   h->finalized = true;
   return IAN_OK;
@@ -1102,6 +1113,7 @@ int ian_destroy(ian_handle* h) {
   for (auto& kv : h->plans) free_plan(kv.second);
   for (auto& w : h->w) { cudaFree(w.b); cudaFree(w.scale); cudaFree(w.shift); }
   cudaFree(h->conv1_wt); cudaFree(h->conv1_b); cudaFree(h->decout_wt); cudaFree(h->decout_tc_wt);
+  cudaFree(h->sk_ws); cudaFree(h->sk_flags);
   cudaFree(h->conv1_tc_wt); if (h->conv1_maps) conv1_free_maps(h->conv1_maps);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }

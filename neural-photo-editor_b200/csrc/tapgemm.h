@@ -79,6 +79,11 @@ struct TapGemm {
   float* out_f32_t;
   int cout_real;
   int passes;                   // 3 = float32 via bf16 hi|lo split (default), 1 = plain bf16 (hi planes only)
+  // stream-K (see WorkIter in tapgemm_tc.cu): per-CTA partial-sum slots [cta][8][32][BN/2] fp32, arrival flags
+  // [cta][8] holding the epoch of the launch that wrote them; sk_ws == nullptr selects whole-tile scheduling
+  float* sk_ws;
+  int* sk_flags;
+  int sk_epoch;
 };
 
 // 128-row M tiles are boxes {Nt images, Ht rows, Wt cols} of the (n, p, q) output grid
@@ -111,5 +116,8 @@ void tc_free_maps(TcMaps*);
 int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st);
 int launch_splitk_finalize(const TapGemm& g, cudaStream_t st);
 int tc_tile_width(const TcMaps* maps);
+int tc_num_sms();
+size_t tc_sk_workspace_floats();   // per handle: 148 slots x 128 x 256 fp32
+size_t tc_sk_flag_ints();
 
 }  // namespace ian

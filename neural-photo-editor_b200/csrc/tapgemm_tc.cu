@@ -20,6 +20,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "tapgemm.h"
 #include "tc_ptx.cuh"
@@ -73,6 +74,10 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { r
 struct WorkItem {
   int phase, ks, co0, it0, it1;
   int n0[2], p0[2], q0[2], mtile[2];   // up to MT = 2 M tiles
+  // stream-K (SK): 0 = the segment is a whole tile; 1 = contributor (a later part of a tile: raw sums go to this
+  // CTA's workspace slot); 2 = finisher (the first part of a tile cut by a CTA boundary: adds the partial sums of
+  // CTAs blockIdx.x+1 .. sk_last, then runs the epilogue)
+  int sk_role, sk_last;
 };
 
 // CH float32 values -> bf16 hi|lo planes (hi only in single-pass mode), packed bf16x2 conversions, 16-byte stores
@@ -128,7 +133,62 @@ __device__ __forceinline__ WorkItem decode_work(const TapGemm& g, const TcMaps& 
   return wi;
 }
 
-template <int BN, int PASSES, int MT>
+// Work iteration of one CTA.  SK = false: whole tiles, w = blockIdx.x + i*gridDim.x (longest phases first).
+// SK = true (stream-K): the launch is ONE linear space of T K-steps over (phase | n-tile | m-tile | K step) and CTA c
+// owns steps [T*c/G, T*(c+1)/G): every SM gets the same tensor work however the tile count divides by 148 and
+// however unequal the phases are.  A tile cut by a CTA boundary is finished by the CTA holding its FIRST K steps
+// (which it reaches at the END of its range), after the CTAs holding the later steps (which they run FIRST) have
+// published their raw partial sums -- an ordered, atomic-free, deterministic fix-up.
+template <int BN, int MT, bool SK>
+struct WorkIter {
+  int w, total, stride;                 // !SK
+  int T, G, cur, end, iters[kMaxPhases], tiles_per_phase, tiles_m, tiles_q, tiles_p;   // SK
+  __device__ __forceinline__ int boundary(int c) const { return (int)((long long)T * c / G); }
+  __device__ __forceinline__ int owner(int gi) const {
+    int c = (int)((long long)gi * G / T);
+    while (c + 1 < G && boundary(c + 1) <= gi) ++c;
+    while (c > 0 && boundary(c) > gi) --c;
+    return c;
+  }
+  __device__ __forceinline__ void init(const TapGemm& g, const TcMaps& maps, int total_work) {
+    if (!SK) { w = blockIdx.x; total = total_work; stride = gridDim.x; return; }
+    T = total_work; G = gridDim.x;
+    tiles_q = g.Wg / maps.Wt; tiles_p = g.Hg / maps.Ht;
+    tiles_m = tiles_q * tiles_p * ((g.n_img + maps.Nt - 1) / maps.Nt);
+    tiles_per_phase = tiles_m * (g.Cout / BN);
+    for (int p = 0; p < kMaxPhases; ++p) iters[p] = p < g.nphase ? g.phase[p].ntaps * (g.Cin / BK) : 0;
+    cur = boundary(blockIdx.x); end = boundary(blockIdx.x + 1);
+  }
+  __device__ __forceinline__ bool next(const TapGemm& g, const TcMaps& maps, WorkItem& wi) {
+    if (!SK) {
+      if (w >= total) return false;
+      wi = decode_work<BN, MT>(g, maps, w);
+      wi.sk_role = 0; wi.sk_last = 0;
+      w += stride;
+      return true;
+    }
+    if (cur >= end) return false;
+    int gi = cur, ph = 0, phase_start = 0;
+    while (ph + 1 < g.nphase && gi >= phase_start + tiles_per_phase * iters[ph]) { phase_start += tiles_per_phase * iters[ph]; ++ph; }
+    const int ip = iters[ph];
+    const int tile = (gi - phase_start) / ip, it = (gi - phase_start) % ip;
+    int len = ip - it;
+    if (len > end - gi) len = end - gi;
+    wi.phase = ph; wi.ks = 0; wi.it0 = it; wi.it1 = it + len;
+    int mt = tile % tiles_m;
+    const int nt = tile / tiles_m;
+    wi.mtile[0] = mt;
+    const int qb = mt % tiles_q; mt /= tiles_q;
+    const int pb = mt % tiles_p; mt /= tiles_p;
+    wi.n0[0] = mt * maps.Nt; wi.p0[0] = pb * maps.Ht; wi.q0[0] = qb * maps.Wt; wi.co0 = nt * BN;
+    wi.sk_role = it > 0 ? 1 : (len < ip ? 2 : 0);
+    wi.sk_last = wi.sk_role == 2 ? owner(phase_start + tile * ip + ip - 1) : 0;
+    cur = gi + len;
+    return true;
+  }
+};
+
+template <int BN, int PASSES, int MT, bool SK>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
   using Cfg = TcCfg<BN, PASSES, MT>;
@@ -171,8 +231,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t i = 0;                                   // running K-step counter across work items
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const WorkItem wi = decode_work<BN, MT>(g, maps, w);
+      WorkIter<BN, MT, SK> iter;
+      iter.init(g, maps, total_work);
+      WorkItem wi;
+      while (iter.next(g, maps, wi)) {
         const Phase ph = g.phase[wi.phase];
         for (int it = wi.it0; it < wi.it1; ++it, ++i) {
           const int s = i % S;
@@ -195,8 +257,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<BN>();
       uint32_t i = 0, t = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
-        const WorkItem wi = decode_work<BN, MT>(g, maps, w);
+      WorkIter<BN, MT, SK> iter;
+      iter.init(g, maps, total_work);
+      WorkItem wi;
+      for (; iter.next(g, maps, wi); ++t) {
         const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
         const uint32_t acc_base = tmem_base + buf * Cfg::kAccCols;
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);    // epilogue has drained this buffer
@@ -246,8 +310,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     const int hl = (ml / maps.Wt) % maps.Ht;
     const int nl = ml / (maps.Wt * maps.Ht);
     uint32_t t = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++t) {
-      const WorkItem wi = decode_work<BN, MT>(g, maps, w);
+    WorkIter<BN, MT, SK> iter;
+    iter.init(g, maps, total_work);
+    WorkItem wi;
+    for (; iter.next(g, maps, wi); ++t) {
       const Phase ph = g.phase[wi.phase];
       const uint32_t buf = t % Cfg::kAccBufs, use = t / Cfg::kAccBufs;
       if (has_cols && g.scale_pix_stride == 0) {         // stage this tile's per-channel scale/shift while the MMAs run
@@ -262,6 +328,18 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
       if (has_cols && wi.it1 > wi.it0) {
+       if (SK && wi.sk_role == 2) {                      // finisher: the later parts were computed first; wait for them
+         for (int k = (int)blockIdx.x + 1 + lane; k <= wi.sk_last; k += 32) {
+           const int* fl = g.sk_flags + k * kEpiWarps + ew;
+           const long long t0 = clock64();
+           int fv;
+           do {
+             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fv) : "l"(fl) : "memory");
+             if (clock64() - t0 > 4000000000LL) __trap();
+           } while (fv != g.sk_epoch);
+         }
+         __syncwarp();
+       }
 #pragma unroll 1
        for (int tj = 0; tj < MT; ++tj) {
         const int n = wi.n0[tj] + nl, p = wi.p0[tj] + hl, q = wi.q0[tj] + wl;
@@ -293,6 +371,22 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+          }
+          if (SK && wi.sk_role == 1) {                   // contributor: raw partial sums -> this CTA's workspace slot
+            float4* wp = reinterpret_cast<float4*>(g.sk_ws + (((long long)blockIdx.x * kEpiWarps + ew) * 32 + lane) * COLS_PER_WARP + cc);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) __stcg(wp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            continue;
+          }
+          if (SK && wi.sk_role == 2) {                   // finisher: add the later parts, in CTA order
+            for (int k = (int)blockIdx.x + 1; k <= wi.sk_last; ++k) {
+              const float4* rp = reinterpret_cast<const float4*>(g.sk_ws + (((long long)k * kEpiWarps + ew) * 32 + lane) * COLS_PER_WARP + cc);
+#pragma unroll
+              for (int j = 0; j < CH / 4; ++j) {
+                const float4 a = __ldcg(rp + j);
+                v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+              }
+            }
           }
           if (g.ksplit > 1) {
             if (valid) {
@@ -368,6 +462,14 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             }
           }
         }
+       }
+       if (SK && wi.sk_role == 1) {                      // publish this warp's sub-block of partial sums
+         __threadfence();
+         __syncwarp();
+         if (lane == 0) {
+           int* fl = g.sk_flags + (int)blockIdx.x * kEpiWarps + ew;
+           asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl), "r"(g.sk_epoch) : "memory");
+         }
        }
       } else {
         tc_fence_before();
@@ -445,42 +547,77 @@ void tc_free_maps(TcMaps* m) { delete m; }
 
 int tc_tile_width(const TcMaps* maps) { return maps->BN; }
 
-template <int BN, int PASSES, int MT>
-static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PASSES, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
-      return -1;
-    attr_set = true;
-  }
-  const int total_work = ((tiles_m + MT - 1) / MT) * (g.Cout / maps->BN) * g.nphase * g.ksplit;
-  const int grid = total_work < num_sms ? total_work : num_sms;
-  tapgemm_tc_kernel<BN, PASSES, MT><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
+int tc_num_sms() {
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  return num_sms;
+}
+size_t tc_sk_workspace_floats() { return (size_t)tc_num_sms() * kEpiWarps * 32 * 128; }
+size_t tc_sk_flag_ints() { return (size_t)tc_num_sms() * kEpiWarps; }
+
+template <int BN, int PASSES, int MT, bool SK>
+static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<BN, PASSES, MT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  int total_work, grid;
+  if (SK) {                                              // T K-steps, one CTA per SM, every CTA gets T/G of them
+    long long T = 0;
+    for (int p = 0; p < g.nphase; ++p) T += (long long)tiles_m * (g.Cout / maps->BN) * g.phase[p].ntaps * (g.Cin / BK);
+    total_work = (int)T;
+    grid = num_sms;
+  } else {
+    total_work = ((tiles_m + MT - 1) / MT) * (g.Cout / maps->BN) * g.nphase * g.ksplit;
+    grid = total_work < num_sms ? total_work : num_sms;
+  }
+  tapgemm_tc_kernel<BN, PASSES, MT, SK><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
+  const int num_sms = tc_num_sms();
   const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
+  const long long tiles = (long long)tiles_m * (g.Cout / maps->BN) * g.nphase;
   // Cout = 128 layers in bf16 mode: pair M tiles on one weight tile (halves the weight refills of these
   // operand-feed-bound layers) once there is enough work to keep every SM busy.  In float32 mode the pair would need
   // all 512 TMEM columns and lose the epilogue overlap -- measured slower, so it keeps single tiles.
-  const bool pair = maps->BN == 128 && g.passes == 1 && g.ksplit == 1 &&
-                    (long long)tiles_m * (g.Cout / 128) * g.nphase >= 2LL * num_sms;
-  if (g.passes == 1) {
-    if (maps->BN == 256) return launch_one<256, 1, 1>(g, maps, tiles_m, num_sms, st);
-    if (maps->BN == 128) return pair ? launch_one<128, 1, 2>(g, maps, tiles_m, num_sms, st) : launch_one<128, 1, 1>(g, maps, tiles_m, num_sms, st);
-    return launch_one<16, 1, 1>(g, maps, tiles_m, num_sms, st);
+  const bool pair = maps->BN == 128 && g.passes == 1 && g.ksplit == 1 && tiles >= 2LL * num_sms;
+  // stream-K pays for one extra partial-sum round trip and one un-overlapped epilogue per CTA, so it is used only where
+  // whole-tile scheduling leaves >= 20 % of the SM-time idle (measured: +14 % on dec_conv1 of IAN_simple, whose 9/6/6/4-tap
+  // phases and 256 tiles map badly onto 148 SMs; -4 % on layers with a 1.16x imbalance).
+  bool sk = false;
+  if (g.sk_ws && g.ksplit == 1 && !pair && maps->BN == 256 && tiles >= num_sms / 2 && !g.out_f32_t) {
+    const int per_phase = tiles_m * (g.Cout / maps->BN);
+    std::vector<long long> load(num_sms, 0);
+    long long T = 0;
+    for (long long w = 0; w < tiles; ++w) {              // the static schedule: tile w -> CTA w % G, phases in order
+      const int it = g.phase[w / per_phase].ntaps * (g.Cin / BK);
+      load[w % num_sms] += it;
+      T += it;
+    }
+    long long makespan = 0;
+    for (long long v : load) makespan = v > makespan ? v : makespan;
+    sk = makespan * num_sms >= (T * 6) / 5;
   }
-  if (maps->BN == 256) return launch_one<256, 3, 1>(g, maps, tiles_m, num_sms, st);
-  if (maps->BN == 128) return launch_one<128, 3, 1>(g, maps, tiles_m, num_sms, st);
-  return launch_one<16, 3, 1>(g, maps, tiles_m, num_sms, st);
+  if (g.passes == 1) {
+    if (maps->BN == 256) return sk ? launch_one<256, 1, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<256, 1, 1, false>(g, maps, tiles_m, num_sms, st);
+    if (maps->BN == 128) {
+      if (pair) return launch_one<128, 1, 2, false>(g, maps, tiles_m, num_sms, st);
+      return sk ? launch_one<128, 1, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<128, 1, 1, false>(g, maps, tiles_m, num_sms, st);
+    }
+    return launch_one<16, 1, 1, false>(g, maps, tiles_m, num_sms, st);
+  }
+  if (maps->BN == 256) return sk ? launch_one<256, 3, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<256, 3, 1, false>(g, maps, tiles_m, num_sms, st);
+  if (maps->BN == 128) return sk ? launch_one<128, 3, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<128, 3, 1, false>(g, maps, tiles_m, num_sms, st);
+  return launch_one<16, 3, 1, false>(g, maps, tiles_m, num_sms, st);
 }
 
 }  // namespace ian
