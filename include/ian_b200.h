@@ -42,7 +42,8 @@ typedef enum ian_status {
 /* Model graph selector.  Replaces `config_module.get_model(dnn=dnn)` (reference API.py:18-21). */
 typedef enum ian_model_kind {
   IAN_MODEL_SIMPLE = 0,   /* reference IAN_simple.py:56-241                                                  */
-  IAN_MODEL_FULL = 1      /* reference IAN.py:67-228: MADE/IAF latent flow, MDC blocks, RGB-Beta head          */
+  IAN_MODEL_FULL = 1,     /* reference IAN.py:67-228: MADE/IAF latent flow, MDC blocks, RGB-Beta head          */
+  IAN_MODEL_V1 = 2        /* reference IANv1.py:63-222: MADE/IAF latent flow, plain deconv decoder, RGB-Beta   */
 } ian_model_kind;
 
 /* Compute path of the dense contractions (enc_conv2-4, dec_conv1-3, fully-connected layers).
@@ -63,7 +64,7 @@ int ian_create(int model_kind, int device, ian_handle** out);
  * GANcheckpoints.py:45-52) an unknown name or a shape mismatch is an error. */
 int ian_set_param(ian_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
 
-/* IAN_MODEL_FULL only: the MADE input ordering (a permutation of 0..99) from which the autoregressive masks are
+/* IAN_MODEL_FULL / IAN_MODEL_V1: the MADE input ordering (a permutation of 0..99) from which the autoregressive masks are
  * derived by integer comparison (reference mask_generator.py:29-38,93-94).  Replaces the one
  * `shuffle_ordering` draw of `l_IAF_mu/ls.reset("Once")` (reference API.py:33-36).  Must precede ian_finalize. */
 int ian_set_made_ordering(ian_handle* h, const int32_t* ordering, int n);

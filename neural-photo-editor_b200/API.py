@@ -87,8 +87,11 @@ class IAN:
         elif base == 'IAN.py':
             # the reference's own API.IAN cannot construct this config (get_model(interp=...) vs dnn=...)
             kind, self.cfg, keys = _lib.IAN_MODEL_FULL, dict(_FULL_CFG), _FULL_MODEL_KEYS
+        elif base == 'IANv1.py':
+            kind, self.cfg, keys = _lib.IAN_MODEL_V1, dict(_FULL_CFG, max_epochs=150), _FULL_MODEL_KEYS
+            self.cfg.pop('ortho', None)                     # IANv1.py:39-61 has no 'ortho' entry
         else:
-            raise NotImplementedError("config %r: the IAN_simple.py and IAN.py graphs are built; IANv1.py is not" % base)
+            raise NotImplementedError("config %r: known graphs are IAN_simple.py, IAN.py and IANv1.py" % base)
         self.kind = kind
         self.weights_fname = str(config_path)[:-3] + '.npz'
         self.model = {k: base[:-3] + '.' + k for k in keys}
@@ -111,7 +114,7 @@ class IAN:
                 continue   # discriminator head: not on the hot path (IAN_simple.py:225-231)
             shape = (C.c_int64 * arr.ndim)(*arr.shape)
             self._check(self._lib.ian_set_param(self._h, name.encode(), _fp(arr), shape, arr.ndim))
-        if kind == _lib.IAN_MODEL_FULL:
+        if kind != _lib.IAN_MODEL_SIMPLE:
             print('Shuffling MADE masks')                   # reference API.py:33-36
             o = np.ascontiguousarray(globals()['made_ordering']() if made_ordering is None else made_ordering, np.int32)
             self.made_ordering = o

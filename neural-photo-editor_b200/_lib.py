@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "libian_b200.so")
 
 IAN_OK = 0
 IAN_PATH_TC, IAN_PATH_SIMT = 0, 1
-IAN_MODEL_SIMPLE, IAN_MODEL_FULL = 0, 1
+IAN_MODEL_SIMPLE, IAN_MODEL_FULL, IAN_MODEL_V1 = 0, 1, 2
 
 _F = C.POINTER(C.c_float)
 _I = C.POINTER(C.c_int32)

@@ -102,6 +102,16 @@ std::vector<Spec> spec_list(int kind) {
       v.push_back({std::string(m) + sub + ".W", {100, 100}});
       v.push_back({std::string(m) + sub + ".b", {100}});
     }
+  if (kind == IAN_MODEL_V1) {                             // IANv1.py:125-201
+    v.push_back({"l_dec_fc2.W", {100, 16384}}); v.push_back({"l_dec_fc2.b", {16384}});
+    v.push_back({"dec_conv1.W", {1024, 512, 5, 5}}); add_bn(v, "bnorm_dc1", 512);
+    v.push_back({"dec_conv2.W", {512, 256, 5, 5}}); add_bn(v, "bnorm_dc2", 256);
+    v.push_back({"dec_conv3.W", {256, 128, 5, 5}}); add_bn(v, "bnorm_dc3", 128);
+    v.push_back({"dec_conv4.W", {128, 64, 5, 5}}); add_bn(v, "bnorm_dc4", 64);
+    add_mdcl(v, "R", 2, 64, {2, 3, 4}); add_mdcl(v, "G_a", 2, 64, {2, 3, 4}); add_mdcl(v, "G_b", 2, 2, {2, 3, 4});
+    add_mdcl(v, "B_a", 2, 64, {2, 3, 4}); add_mdcl(v, "B_b", 2, 4, {2, 3, 4});
+    return v;
+  }
   v.push_back({"l_dec_fc2.W", {100, 8192}}); v.push_back({"l_dec_fc2.b", {8192}});
   v.push_back({"dec_conv1.W", {512, 512, 5, 5}});
   add_mdblock(v, "dec_conv2a", 512, {0, 2});
@@ -188,6 +198,8 @@ struct ian_handle {
 };
 
 namespace {
+
+inline bool has_flow(const ian_handle* h) { return h->model_kind != IAN_MODEL_SIMPLE; }   // MADE/IAF latent + RGB-Beta head
 
 int fail(ian_handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -392,6 +404,34 @@ int finish_maps(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
   return IAN_OK;
 }
 
+// decoder of IANv1 (reference IANv1.py:125-201): dense (linear) -> 4 x [deconv, BN, relu] -> RGB-Beta head.  The last deconv
+// has 64 output channels; it is stored 128 wide (upper half zero weights) so the head GEMM keeps Cin % 64 == 0 tiles.
+int build_plan_v1(ian_handle* h, Plan* pl, Plan** out) {
+  TapGemm* g = pl->g;
+  const int n = pl->n;
+  auto outp = [](TapGemm& gg, const Planes& t) { gg.out = t.p; gg.out_plane = t.plane; };
+  set_io(g[L_DEC_FC2], pl->zp, n, 1, 1, 128, 1, 1, h->w[L_DEC_FC2], 1, 1); taps_dense(g[L_DEC_FC2]);
+  g[L_DEC_FC2].act = ACT_NONE; outp(g[L_DEC_FC2], pl->h0);
+  set_io(g[L_DEC_CONV1], pl->h0, n, 4, 4, 1024, 4, 4, h->w[L_DEC_CONV1], 8, 8); taps_deconv_s2(g[L_DEC_CONV1]);
+  g[L_DEC_CONV1].act = ACT_RELU; outp(g[L_DEC_CONV1], pl->h1);
+  set_io(g[L_DEC_CONV2], pl->h1, n, 8, 8, 512, 8, 8, h->w[L_DEC_CONV2], 16, 16); taps_deconv_s2(g[L_DEC_CONV2]);
+  g[L_DEC_CONV2].act = ACT_RELU; outp(g[L_DEC_CONV2], pl->h2);
+  set_io(g[L_DEC_CONV3], pl->h2, n, 16, 16, 256, 16, 16, h->w[L_DEC_CONV3], 32, 32); taps_deconv_s2(g[L_DEC_CONV3]);
+  g[L_DEC_CONV3].act = ACT_RELU; outp(g[L_DEC_CONV3], pl->h3);
+  set_io(g[F_DEC_CONV4], pl->h3, n, 32, 32, 128, 32, 32, h->w[F_DEC_CONV4], 64, 64); taps_deconv_s2(g[F_DEC_CONV4]);
+  g[F_DEC_CONV4].act = ACT_RELU; outp(g[F_DEC_CONV4], pl->fh4);
+  set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
+  g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
+  int rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
+                                           L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4});
+  if (rc != IAN_OK) return rc;
+  rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2,
+                           L_DEC_CONV3, F_DEC_CONV4, F_HEAD});
+  if (rc != IAN_OK) return rc;
+  *out = pl;
+  return IAN_OK;
+}
+
 // decoder of the full IAN (reference IAN.py:129-207): dense -> 3 x (deconv, MDBLOCK) -> deconv -> RGB-Beta head
 int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
   TapGemm* g = pl->g;
@@ -439,12 +479,17 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   int rc;
 #define AP(t, e) if ((rc = alloc_planes(h, pl, pl->t, (e))) != IAN_OK) return rc;
 #define AB(t, e) if ((rc = alloc_buf(h, pl, pl->t, (e))) != IAN_OK) return rc;
-  const bool full = h->model_kind == IAN_MODEL_FULL;
+  const bool full = h->model_kind == IAN_MODEL_FULL, v1 = h->model_kind == IAN_MODEL_V1;
   AP(a1, N * 32 * 32 * 128) AP(a2, N * 16 * 16 * 256) AP(a3, N * 8 * 8 * 512) AP(a4, N * 4 * 4 * 1024)
   AP(f1, N * 1024) AP(zp, N * 128)
   AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(ws_fc1, N * 1024) AB(eps, N * 100)
   if (!full) {
     AP(h0, N * 16384) AP(h1, N * 8 * 8 * 512) AP(h2, N * 16 * 16 * 256) AP(h3, N * 32 * 32 * 128)
+  }
+  if (v1) {
+    AP(fh4, N * 4096 * 128)
+    AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4) AB(tt, N * 198 * 4096)
+  } else if (!full) {
     AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
     AB(gpad, N * 128) AB(target, N * 3 * 4096) AB(boxes, N * 4)
   } else {
@@ -468,11 +513,12 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   set_io(g[L_ENC_CONV4], pl->a3, n, 8, 8, 512, 4, 4, h->w[L_ENC_CONV4], 4, 4); taps_conv_s2(g[L_ENC_CONV4]);
   g[L_ENC_CONV4].act = ACT_LRELU; g[L_ENC_CONV4].out = pl->a4.p; g[L_ENC_CONV4].out_plane = pl->a4.plane;
   set_io(g[L_ENC_FC1], pl->a4, n, 1, 1, 16384, 1, 1, h->w[L_ENC_FC1], 1, 1); taps_dense(g[L_ENC_FC1]);
-  g[L_ENC_FC1].act = full ? ACT_RELU : ACT_ELU;   // IAN.py:118 uses rectify, IAN_simple.py:121 elu
+  g[L_ENC_FC1].act = has_flow(h) ? ACT_RELU : ACT_ELU;   // IAN.py:118 / IANv1.py:109 use rectify, IAN_simple.py:121 elu
   g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ws = pl->ws_fc1;
   set_io(g[L_ENC_HEAD], pl->f1, n, 1, 1, 1024, 1, 1, h->w[L_ENC_HEAD], 1, 1); taps_dense(g[L_ENC_HEAD]);
   g[L_ENC_HEAD].act = ACT_NONE; g[L_ENC_HEAD].out_f32 = pl->head;
   if (full) return build_plan_full(h, pl, out);
+  if (v1) return build_plan_v1(h, pl, out);
   // ---- decoder (IAN_simple.py:129-170)
   set_io(g[L_DEC_FC2], pl->zp, n, 1, 1, 128, 1, 1, h->w[L_DEC_FC2], 1, 1); taps_dense(g[L_DEC_FC2]);
   g[L_DEC_FC2].act = ACT_RELU; g[L_DEC_FC2].out = pl->h0.p; g[L_DEC_FC2].out_plane = pl->h0.plane;
@@ -592,7 +638,7 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
   int rc;
   for (int l : {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-  if (h->model_kind == IAN_MODEL_FULL) {
+  if (has_flow(h)) {
     // l_Z_IAF = mu (+ exp(ls) eps), then l_Z = IAF(l_Z_IAF; MADE_mu, MADE_ls)   (IAN.py:126-128)
     LAUNCH_TRY(h, launch_sample(pl->head, eps, z_pre ? z_pre : pl->z0, nullptr, 0, n, st));
     LAUNCH_TRY(h, launch_made_iaf(z_pre ? z_pre : pl->z0, h->made_w, h->made_b, z, pl->zp.p, pl->zp.plane, n, st));
@@ -606,6 +652,13 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
 // zp must already hold the latent planes
 int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
   int rc;
+  if (h->model_kind == IAN_MODEL_V1) {
+    for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4, F_HEAD})
+      if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
+    LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
+    return IAN_OK;
+  }
   if (h->model_kind == IAN_MODEL_FULL) {
     for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
@@ -901,9 +954,7 @@ void mdc_composite(ian_handle* h, const std::string& name, int F, int C, const s
   }
 }
 
-int prepare_full_decoder(ian_handle* h) {
-  int rc;
-  std::vector<float> B, sc, sf, comp;
+int prepare_made(ian_handle* h) {
   // ---- MADE (layers.py:653-853): masks from the ordering (mask_generator.py:93-94), integer
   // comparisons, multiplied into the float32 weights here on the host (bit-exact W*M)
   {
@@ -929,6 +980,90 @@ int prepare_full_decoder(ian_handle* h) {
     CUDA_TRY(h, cudaMalloc((void**)&h->made_b, mb.size() * 4));
     CUDA_TRY(h, cudaMemcpy(h->made_b, mb.data(), mb.size() * 4, cudaMemcpyHostToDevice));
   }
+  return IAN_OK;
+}
+
+// RGB-Beta head weights for a feature map with C real channels (128 for IAN.py, 64 for IANv1.py) stored 128 wide
+int prepare_head(ian_handle* h, int C) {
+  int rc;
+  std::vector<float> B, sc, comp;
+  // ---- RGB-Beta head (IAN.py:183-207): the three 128->2 MDC convs as one 16-row tile [R | G_a | B_a | 0...]
+  {
+    const std::vector<int> hs = {2, 3, 4};
+    const auto off = mdc_offsets(hs);
+    const int nt = (int)off.size();
+    if (nt * 6 != 198) return fail(h, IAN_ERR_STATE, "unexpected head tap count %d", nt);
+    // one weight tile [256 rows][128]: row t*6 + (2k+f) = composite tap t of filter f of conv k in {R, G_a, B_a}
+    B.assign((size_t)256 * 128, 0.f);
+    const char* names[3] = {"R", "G_a", "B_a"};
+    for (int k = 0; k < 3; ++k) {
+      mdc_composite(h, names[k], 2, C, hs, comp);
+      for (int t = 0; t < nt; ++t)
+        for (int f = 0; f < 2; ++f)
+          for (int c = 0; c < C; ++c) B[((size_t)(t * 6 + 2 * k + f)) * 128 + c] = comp[((size_t)t * 2 + f) * C + c];
+    }
+    sc.assign(256, 1.f);
+    if ((rc = upload_gemm_weights(h, F_HEAD, B, 1, 256, 128, sc, {})) != IAN_OK) return rc;
+    std::vector<int> taps(nt * 2);
+    for (int t = 0; t < nt; ++t) { taps[2 * t] = off[t].first; taps[2 * t + 1] = off[t].second; }
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_taps, taps.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+    h->head_ntaps = nt;
+    mdc_composite(h, "G_b", 2, 2, hs, comp);             // [nt][2 out][2 in]
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_wgb, comp.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_wgb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
+    mdc_composite(h, "B_b", 2, 4, hs, comp);             // [nt][2 out][4 in]
+    CUDA_TRY(h, cudaMalloc((void**)&h->head_wbb, comp.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->head_wbb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return IAN_OK;
+}
+
+// IANv1 decoder weights (IANv1.py:125-175)
+int prepare_v1_decoder(ian_handle* h) {
+  int rc;
+  std::vector<float> B, sc, sf;
+  if ((rc = prepare_made(h)) != IAN_OK) return rc;
+  {   // l_dec_fc2: dense 100 -> 16384 + bias, NO nonlinearity; column j = c*16+hw -> hw*1024 + c
+    const auto& W = P(h, "l_dec_fc2.W").data;
+    const auto& b = P(h, "l_dec_fc2.b").data;
+    B.assign((size_t)16384 * 128, 0.f);
+    sc.assign(16384, 1.f);
+    sf.assign(16384, 0.f);
+    for (int c = 0; c < 1024; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 1024 + c;
+        sf[col] = b[j];
+        for (int k = 0; k < 100; ++k) B[(size_t)col * 128 + k] = W[(size_t)k * 16384 + j];
+      }
+    if ((rc = upload_gemm_weights(h, L_DEC_FC2, B, 1, 16384, 128, sc, sf)) != IAN_OK) return rc;
+  }
+  struct St { int l; const char* w; const char* bn; int Cin, Cout; } sts[3] = {
+      {L_DEC_CONV1, "dec_conv1.W", "bnorm_dc1", 1024, 512}, {L_DEC_CONV2, "dec_conv2.W", "bnorm_dc2", 512, 256},
+      {L_DEC_CONV3, "dec_conv3.W", "bnorm_dc3", 256, 128}};
+  for (const St& s : sts) {
+    deconv_fwd_tiles(P(h, s.w).data, s.Cin, s.Cout, B);
+    fold_bn(h, s.bn, s.Cout, sc, sf);
+    if ((rc = upload_gemm_weights(h, s.l, B, 25, s.Cout, s.Cin, sc, sf)) != IAN_OK) return rc;
+  }
+  {   // dec_conv4: 128 -> 64 channels, stored 128 wide: channels 64..127 have zero weights, scale and shift (relu(0) = 0)
+    const auto& W = P(h, "dec_conv4.W").data;
+    B.assign((size_t)25 * 128 * 128, 0.f);
+    for (int ci = 0; ci < 128; ++ci)
+      for (int co = 0; co < 64; ++co)
+        for (int t = 0; t < 25; ++t) B[((size_t)t * 128 + co) * 128 + ci] = W[((size_t)ci * 64 + co) * 25 + t];
+    fold_bn(h, "bnorm_dc4", 64, sc, sf);
+    sc.resize(128, 0.f);
+    sf.resize(128, 0.f);
+    if ((rc = upload_gemm_weights(h, F_DEC_CONV4, B, 25, 128, 128, sc, sf)) != IAN_OK) return rc;
+  }
+  return prepare_head(h, 64);
+}
+
+int prepare_full_decoder(ian_handle* h) {
+  int rc;
+  std::vector<float> B, sc, sf, comp;
+  if ((rc = prepare_made(h)) != IAN_OK) return rc;
   // ---- l_dec_fc2: dense 100 -> 8192 + bias, lrelu (IAN.py:129-134); column j = c*16+hw -> hw*512 + c
   {
     const auto& W = P(h, "l_dec_fc2.W").data;
@@ -964,35 +1099,7 @@ int prepare_full_decoder(ian_handle* h) {
   deconv_fwd_tiles(P(h, "dec_conv4.W").data, 128, 128, B);
   fold_bn(h, "bnorm_dc4", 128, sc, sf);
   if ((rc = upload_gemm_weights(h, F_DEC_CONV4, B, 25, 128, 128, sc, sf)) != IAN_OK) return rc;
-  // ---- RGB-Beta head (IAN.py:183-207): the three 128->2 MDC convs as one 16-row tile [R | G_a | B_a | 0...]
-  {
-    const std::vector<int> hs = {2, 3, 4};
-    const auto off = mdc_offsets(hs);
-    const int nt = (int)off.size();
-    if (nt * 6 != 198) return fail(h, IAN_ERR_STATE, "unexpected head tap count %d", nt);
-    // one weight tile [256 rows][128]: row t*6 + (2k+f) = composite tap t of filter f of conv k in {R, G_a, B_a}
-    B.assign((size_t)256 * 128, 0.f);
-    const char* names[3] = {"R", "G_a", "B_a"};
-    for (int k = 0; k < 3; ++k) {
-      mdc_composite(h, names[k], 2, 128, hs, comp);
-      for (int t = 0; t < nt; ++t)
-        for (int f = 0; f < 2; ++f)
-          for (int c = 0; c < 128; ++c) B[((size_t)(t * 6 + 2 * k + f)) * 128 + c] = comp[((size_t)t * 2 + f) * 128 + c];
-    }
-    sc.assign(256, 1.f);
-    if ((rc = upload_gemm_weights(h, F_HEAD, B, 1, 256, 128, sc, {})) != IAN_OK) return rc;
-    std::vector<int> taps(nt * 2);
-    for (int t = 0; t < nt; ++t) { taps[2 * t] = off[t].first; taps[2 * t + 1] = off[t].second; }
-    CUDA_TRY(h, cudaMalloc((void**)&h->head_taps, taps.size() * 4));
-    CUDA_TRY(h, cudaMemcpy(h->head_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
-    h->head_ntaps = nt;
-    mdc_composite(h, "G_b", 2, 2, hs, comp);             // [nt][2 out][2 in]
-    CUDA_TRY(h, cudaMalloc((void**)&h->head_wgb, comp.size() * 4));
-    CUDA_TRY(h, cudaMemcpy(h->head_wgb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
-    mdc_composite(h, "B_b", 2, 4, hs, comp);             // [nt][2 out][4 in]
-    CUDA_TRY(h, cudaMalloc((void**)&h->head_wbb, comp.size() * 4));
-    CUDA_TRY(h, cudaMemcpy(h->head_wbb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
-  }
+  if ((rc = prepare_head(h, 128)) != IAN_OK) return rc;
   return IAN_OK;
 }
 
@@ -1023,7 +1130,7 @@ extern "C" {
 
 int ian_create(int model_kind, int device, ian_handle** out) {
   if (!out) return fail(nullptr, IAN_ERR_INVALID, "out is NULL");
-  if (model_kind != IAN_MODEL_SIMPLE && model_kind != IAN_MODEL_FULL)
+  if (model_kind != IAN_MODEL_SIMPLE && model_kind != IAN_MODEL_FULL && model_kind != IAN_MODEL_V1)
     return fail(nullptr, IAN_ERR_UNSUPPORTED, "unknown model kind %d", model_kind);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1094,7 +1201,8 @@ int ian_finalize(ian_handle* h) {
   DeviceGuard dg(h->device);
   int rc = prepare_encoder(h);
   if (rc != IAN_OK) return rc;
-  rc = h->model_kind == IAN_MODEL_FULL ? prepare_full_decoder(h) : prepare_simple_decoder(h);
+  rc = h->model_kind == IAN_MODEL_FULL ? prepare_full_decoder(h)
+       : h->model_kind == IAN_MODEL_V1 ? prepare_v1_decoder(h) : prepare_simple_decoder(h);
   if (rc != IAN_OK) return rc;
   CUDA_TRY(h, cudaMalloc((void**)&h->sk_ws, tc_sk_workspace_floats() * sizeof(float)));
   CUDA_TRY(h, cudaMalloc((void**)&h->sk_flags, tc_sk_flag_ints() * sizeof(int)));
@@ -1141,8 +1249,8 @@ int ian_set_path(ian_handle* h, int path) {
 int ian_set_precision(ian_handle* h, int precision) {
   if (!h) return IAN_ERR_INVALID;
   if (precision != IAN_PRECISION_FP32 && precision != IAN_PRECISION_BF16) return fail(h, IAN_ERR_INVALID, "unknown precision %d", precision);
-  if (precision == IAN_PRECISION_BF16 && h->model_kind != IAN_MODEL_FULL)
-    return fail(h, IAN_ERR_UNSUPPORTED, "bf16 mode is built for the full IAN graph (BASELINE configs[2]); IAN_simple runs in float32");
+  if (precision == IAN_PRECISION_BF16 && h->model_kind == IAN_MODEL_SIMPLE)
+    return fail(h, IAN_ERR_UNSUPPORTED, "bf16 mode is built for the IAN.py / IANv1.py graphs (BASELINE configs[2]); IAN_simple runs in float32");
   h->passes = precision == IAN_PRECISION_BF16 ? 1 : 3;
   return IAN_OK;
 }
@@ -1460,7 +1568,7 @@ int ian_flow_host(ian_handle* h, const float* z_iaf, int n, float* z_out /*nulla
   cudaStream_t st = h->stream;
   rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
     CUDA_TRY(h, cudaMemcpyAsync(pl->eps, z_iaf + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
-    if (h->model_kind == IAN_MODEL_FULL)
+    if (has_flow(h))
       LAUNCH_TRY(h, launch_made_iaf(pl->eps, h->made_w, h->made_b, pl->z, pl->zp.p, pl->zp.plane, cn, st));
     else {
       CUDA_TRY(h, cudaMemcpyAsync(pl->z, pl->eps, (size_t)cn * 400, cudaMemcpyDeviceToDevice, st));

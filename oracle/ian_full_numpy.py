@@ -147,3 +147,21 @@ def full_decode(P, z):
     G = on.sigmoid(mdcl(P, "G_a", h, sc) + mdcl(P, "G_b", R, sc))
     B = on.sigmoid(mdcl(P, "B_a", h, sc) + mdcl(P, "B_b", np.concatenate([R, G], 1), sc))
     return np.stack([beta(R[:, 0], R[:, 1]), beta(G[:, 0], G[:, 1]), beta(B[:, 0], B[:, 1])], 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# IANv1 graph (reference IANv1.py:63-222): same encoder + MADE/IAF latent as IAN.py; decoder without MDC blocks
+# ----------------------------------------------------------------------------------------------
+
+def v1_decode(P, z):
+    """IANv1.py:125-201: dense 100->16384 (+bias, linear) -> 4 x [deconv -> BN -> relu] (1024->512->256->128->64)
+    -> RGB-Beta head on 64 channels."""
+    z = np.asarray(z, F64)
+    h = on.dense(z, P["l_dec_fc2.W"], P["l_dec_fc2.b"]).reshape(-1, 1024, 4, 4)       # nonlinearity=None (IANv1.py:127)
+    for i, name in ((1, "bnorm_dc1"), (2, "bnorm_dc2"), (3, "bnorm_dc3"), (4, "bnorm_dc4")):
+        h = on.rectify(on.batchnorm_inf(on.deconv5x5_s2(h, P["dec_conv%d.W" % i]), on._bn(P, name)))
+    sc = [2, 3, 4]
+    R = on.sigmoid(mdcl(P, "R", h, sc))
+    G = on.sigmoid(mdcl(P, "G_a", h, sc) + mdcl(P, "G_b", R, sc))
+    B = on.sigmoid(mdcl(P, "B_a", h, sc) + mdcl(P, "B_b", np.concatenate([R, G], 1), sc))
+    return np.stack([beta(R[:, 0], R[:, 1]), beta(G[:, 0], G[:, 1]), beta(B[:, 0], B[:, 1])], 1)

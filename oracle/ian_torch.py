@@ -198,3 +198,18 @@ def full_decode(P, z, mdcl_fn=mdcl):
     def beta(a, b):
         return 2.0 * (a / (a + b + 1e-8)) - 1.0
     return torch.stack([beta(R[:, 0], R[:, 1]), beta(G[:, 0], G[:, 1]), beta(B[:, 0], B[:, 1])], 1)
+
+
+def v1_decode(P, z, mdcl_fn=mdcl):
+    """IANv1.py:125-201 (see ian_full_numpy.v1_decode)."""
+    h = (z @ P["l_dec_fc2.W"] + P["l_dec_fc2.b"]).reshape(-1, 1024, 4, 4)
+    for i, name in ((1, "bnorm_dc1"), (2, "bnorm_dc2"), (3, "bnorm_dc3"), (4, "bnorm_dc4")):
+        h = _relu(_bn(P, name, deconv(h, P["dec_conv%d.W" % i])))
+    sc = [2, 3, 4]
+    R = torch.sigmoid(mdcl_fn(P, "R", h, sc))
+    G = torch.sigmoid(mdcl_fn(P, "G_a", h, sc) + mdcl_fn(P, "G_b", R, sc))
+    B = torch.sigmoid(mdcl_fn(P, "B_a", h, sc) + mdcl_fn(P, "B_b", torch.cat([R, G], 1), sc))
+
+    def beta(a, b):
+        return 2.0 * (a / (a + b + 1e-8)) - 1.0
+    return torch.stack([beta(R[:, 0], R[:, 1]), beta(G[:, 0], G[:, 1]), beta(B[:, 0], B[:, 1])], 1)

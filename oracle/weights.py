@@ -105,3 +105,37 @@ def make_full_weights(seed=0, w_std=0.02):
             std = 0.05 if (name.endswith("W") and not name.endswith(".W")) else w_std
             P[name] = rng.normal(0, std, shp).astype(np.float32)
     return P
+
+
+# ---- IANv1 (reference IANv1.py:63-222) ----------------------------------------------------------------
+def v1_shapes():
+    full = full_shapes()
+    enc_made = [s for s in full if s[0].startswith(("enc_", "bnorm2", "bnorm3", "bnorm4", "bnorm_enc", "mu_", "ls_", "l_IAF"))]
+    dec = [("l_dec_fc2.W", (100, 16384)), ("l_dec_fc2.b", (16384,)),
+           ("dec_conv1.W", (1024, 512, 5, 5)), ("bnorm_dc1", 512), ("dec_conv2.W", (512, 256, 5, 5)), ("bnorm_dc2", 256),
+           ("dec_conv3.W", (256, 128, 5, 5)), ("bnorm_dc3", 128), ("dec_conv4.W", (128, 64, 5, 5)), ("bnorm_dc4", 64)]
+    sc = [2, 3, 4]
+    dec += (_mdcl_shapes("R", 2, 64, sc) + _mdcl_shapes("G_a", 2, 64, sc) + _mdcl_shapes("G_b", 2, 2, sc) +
+            _mdcl_shapes("B_a", 2, 64, sc) + _mdcl_shapes("B_b", 2, 4, sc))
+    return enc_made + dec
+
+
+def make_v1_weights(seed=0, w_std=0.02):
+    rng = np.random.default_rng(seed)
+    P = {}
+    for name, shp in v1_shapes():
+        if isinstance(shp, int):
+            P[name + ".gamma"] = rng.uniform(0.5, 1.5, shp).astype(np.float32)
+            P[name + ".beta"] = rng.normal(0, 0.1, shp).astype(np.float32)
+            P[name + ".mean"] = rng.normal(0, 0.1, shp).astype(np.float32)
+            P[name + ".inv_std"] = rng.uniform(0.5, 2.0, shp).astype(np.float32)
+        elif shp[0] == "coeff":
+            P[name] = rng.uniform(0.1, 0.5, shp[1]).astype(np.float32)
+        elif shp[0] == "made":
+            P[name] = rng.normal(0, 0.1, shp[1]).astype(np.float32)
+        elif name in ("enc_conv1.b", "l_dec_fc2.b"):
+            P[name] = rng.normal(0, 0.02 if name == "enc_conv1.b" else 0.2, shp).astype(np.float32)
+        else:
+            std = 0.05 if (name.endswith("W") and not name.endswith(".W")) else (0.1 if name == "l_dec_fc2.W" else w_std)
+            P[name] = rng.normal(0, std, shp).astype(np.float32)
+    return P

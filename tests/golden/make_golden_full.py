@@ -38,6 +38,16 @@ def main():
                         mu=mu, logsigma=ls, z=z, eps=eps, z_sample=z_sample, xhat=xhat.astype(np.float32), z_rand=z_rand,
                         xhat_rand=xhat_rand.astype(np.float32))
     print('wrote', out, os.path.getsize(out), 'bytes')
+    # ---- IANv1 (IANv1.py graph): same encoder/flow code path, different decoder
+    Pv = ow.make_v1_weights(WEIGHT_SEED)
+    mu1, ls1 = fn.full_encode_mu_ls(Pv, x)
+    z1 = fn.full_latent(Pv, mu1, masks)
+    xh1 = fn.v1_decode(Pv, z1.astype(np.float32))
+    xr1 = fn.v1_decode(Pv, z_rand)
+    out1 = os.path.join(ROOT, 'tests', 'golden', 'ian_v1_golden.npz')
+    np.savez_compressed(out1, weight_seed=WEIGHT_SEED, images=imgs, ordering=ordering.astype(np.int32), mu=mu1, z=z1,
+                        xhat=xh1.astype(np.float32), z_rand=z_rand, xhat_rand=xr1.astype(np.float32))
+    print('wrote', out1, os.path.getsize(out1), 'bytes')
 
 
 if __name__ == '__main__':

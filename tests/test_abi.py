@@ -55,7 +55,7 @@ def test_input_filtering_matches_theano_rules(npe):
 
 def test_unknown_config_is_rejected(npe, weights):
     with pytest.raises(NotImplementedError):
-        npe.IAN("IANv1.py", True, weights=weights)
+        npe.IAN("IAN_v2.py", True, weights=weights)
 
 
 def test_made_ordering_host_logic_matches_oracle(npe):

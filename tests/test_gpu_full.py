@@ -106,10 +106,10 @@ def test_sample_ian_function_set(full_model, gold, PF):
 
 def test_simple_model_function_set_is_flowless(model, golden):
     x = on.to_tanh(golden["images"][:2].astype(np.float64)).astype(np.float32)
-    assert np.abs(model.Zfn(x) - model.encode_images(x)).max() <= 2e-5
+    assert np.abs(model.Zfn(x) - model.encode_images(x)).max() <= 2e-4     # two runs: atomic split-K summation order
     z = golden["z_rand"][:2]
     assert np.array_equal(model.Z_IAF_fn(z), z)
-    assert np.abs(model.sample(z) - model.sample_at(z)).max() <= 2e-5
+    assert np.abs(model.sample(z) - model.sample_at(z)).max() <= 5e-5
 
 
 def test_bf16_mode_tolerance_vs_oracle(full_model, gold):
@@ -138,3 +138,29 @@ def test_bf16_mode_tolerance_vs_oracle(full_model, gold):
 def test_bf16_mode_is_full_model_only(model, npe):
     with pytest.raises(npe.IanError):
         model.set_precision("bf16")
+
+
+# ---- IANv1.py graph -----------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gold_v1():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ian_v1_golden.npz")))
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_ianv1_golden(npe, gold_v1, path):
+    P1 = ow.make_v1_weights(int(gold_v1["weight_seed"]))
+    m = npe.IAN("IANv1.py", dnn=True, weights=P1, path=path)
+    try:
+        x = on.to_tanh(gold_v1["images"].astype(np.float64)).astype(np.float32)
+        z = m.encode_images(x)
+        assert _zclose(z, gold_v1["z"]), np.abs(z - gold_v1["z"]).max()
+        assert np.abs(m.Zfn(x) - gold_v1["mu"]).max() <= 2e-4
+        xh = m.sample_at(gold_v1["z_rand"])
+        assert np.abs(xh - gold_v1["xhat_rand"]).max() <= 2e-4
+        assert np.abs(m.sample_at(gold_v1["z"].astype(np.float32)) - gold_v1["xhat"]).max() <= 2e-4
+        if path == "tc":
+            m.set_precision("bf16")
+            err = np.abs(m.sample_at(gold_v1["z_rand"]) - gold_v1["xhat_rand"])
+            assert err.max() <= 0.2 and err.mean() <= 8e-3
+    finally:
+        m.close()

@@ -71,3 +71,11 @@ def test_numpy_vs_torch_and_golden(PF, gold):
     assert np.abs(xh - gold["xhat_rand"][:1]).max() < 1e-6          # golden stored as float32
     xn = fn.full_decode(PF, gold["z_rand"][:1])
     assert np.abs(xn - xh).max() < 1e-12
+
+
+def test_v1_numpy_vs_torch():
+    P1 = ow.make_v1_weights(0)
+    z = np.random.default_rng(3).standard_normal((1, 100)).astype(np.float32)
+    a = fn.v1_decode(P1, z)
+    b = ot.v1_decode(ot.to_torch(P1, torch.float64), torch.from_numpy(z).double()).numpy()
+    assert np.abs(a - b).max() < 1e-12 and a.shape == (1, 3, 64, 64)
