@@ -347,7 +347,7 @@ def main():
 
     # ---- secondary metric: latent-edit steps/sec (BASELINE configs[3])
     edit = None
-    if not args.no_edit:
+    if not args.no_edit and world == 1:                      # secondary blocks are single-GPU measurements
         r2 = np.random.default_rng(2)
         ze = torch.from_numpy(r2.standard_normal((EDIT_BATCH, 100)).astype(np.float32)).to(dev)
         r3 = np.random.default_rng(3)
@@ -372,7 +372,7 @@ def main():
 
     # ---- BASELINE configs[0] size: one image, encode -> decode, through the synchronous host API (NPE's call pattern)
     lat = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         x1 = x_np[:1].copy()
         for _ in range(5):
             model.reconstruct(x1)
@@ -386,7 +386,7 @@ def main():
 
     # ---- secondary block: full IAN (reference IAN.py graph), BASELINE configs[2] size (batch 512)
     full = None
-    if not args.no_full and rank == 0:
+    if not args.no_full and rank == 0 and world == 1:
         fm = pkg.IAN("IAN.py", dnn=True, weights=ow.make_full_weights(0), device=local_rank)
         FB = 512
         xf = torch.from_numpy(np.random.default_rng(77).uniform(-1, 1, (FB, 3, 64, 64)).astype(np.float32)).to(dev)
