@@ -33,6 +33,7 @@ struct TcMaps {
   CUtensorMap a1[4];    // same tensors, hi plane only (single-pass bf16 mode)
   CUtensorMap b1;
   int Wt, Ht, Nt, BN;
+  mutable int sk_choice;   // cached stream-K decision of launch_tapgemm_tc: -1 unknown, 0 whole tiles, 1 stream-K
 };
 
 namespace {
@@ -493,6 +494,7 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen) {
   TcMaps* m = new TcMaps();
   memset(m, 0, sizeof(*m));
   tile_shape(g.Hg, g.Wg, m->Wt, m->Ht, m->Nt);
+  m->sk_choice = -1;
   m->BN = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
   if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
     snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
@@ -594,7 +596,9 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
   // whole-tile scheduling leaves >= 20 % of the SM-time idle (measured: +14 % on dec_conv1 of IAN_simple, whose 9/6/6/4-tap
   // phases and 256 tiles map badly onto 148 SMs; -4 % on layers with a 1.16x imbalance).
   bool sk = false;
-  if (g.sk_ws && g.ksplit == 1 && !pair && maps->BN == 256 && tiles >= num_sms / 2 && !g.out_f32_t) {
+  if (maps->sk_choice >= 0) {
+    sk = maps->sk_choice == 1 && g.sk_ws != nullptr;
+  } else if (g.sk_ws && g.ksplit == 1 && !pair && maps->BN == 256 && tiles >= num_sms / 2 && !g.out_f32_t) {
     const int per_phase = tiles_m * (g.Cout / maps->BN);
     std::vector<long long> load(num_sms, 0);
     long long T = 0;
@@ -606,6 +610,9 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
     long long makespan = 0;
     for (long long v : load) makespan = v > makespan ? v : makespan;
     sk = makespan * num_sms >= (T * 6) / 5;
+    maps->sk_choice = sk ? 1 : 0;
+  } else if (g.sk_ws) {
+    maps->sk_choice = 0;
   }
   if (g.passes == 1) {
     if (maps->BN == 256) return sk ? launch_one<256, 1, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<256, 1, 1, false>(g, maps, tiles_m, num_sms, st);
