@@ -232,7 +232,7 @@ struct Planes {               // NHWC split-plane activation tensor
 struct Plan {
   int n = 0;
   Planes a1, a2, a3, a4, f1, zp, h0, h1, h2, h3, d3, d2, d1, d0;
-  float *x = nullptr, *head = nullptr, *z = nullptr, *xhat = nullptr, *gpad = nullptr, *ws_fc1 = nullptr, *eps = nullptr;
+  float *x = nullptr, *head = nullptr, *z = nullptr, *xhat = nullptr, *gpad = nullptr, *eps = nullptr;
   float* target = nullptr;
   int32_t* boxes = nullptr;
   // full IAN activations (NHWC split planes): block input x, pre-activated t0, mid t2, block output y per scale
@@ -369,25 +369,33 @@ int choose_ksplit(const TapGemm& g) {
 }
 
 // Small batches (NPE runs batch 1): a layer with fewer tiles than SMs would stream its weights through a handful of
-// SMs.  Give every such layer the plan's shared split-K workspace so choose_ksplit() can spread K over the chip.
-int assign_splitk_workspace(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
-  long long need = 0;
-  std::vector<int> small;
+// SMs.  Mark every such layer (ksplit = 0: "choose") so choose_ksplit() can spread K over the chip.
+void mark_splitk_candidates(Plan* pl, std::initializer_list<int> layers) {
   for (int l : layers) {
     TapGemm& g = pl->g[l];
     if (g.out_f32_t) continue;
     const int bn = (g.Cout % 256 == 0) ? 256 : (g.Cout % 128 == 0) ? 128 : 16;
     const long long tiles = (long long)((g.n_img * g.Hg * g.Wg + 127) / 128) * (g.Cout / bn) * g.nphase;
-    if (tiles > 74) continue;
-    small.push_back(l);
-    const long long sz = (long long)g.n_img * g.Hout * g.Wout * g.Cout;
-    if (sz > need) need = sz;
+    if (tiles <= 74) g.ksplit = 0;
   }
-  if (small.empty()) return IAN_OK;
+}
+
+// One workspace per plan, shared by its split-K layers (they run back to back on one stream):
+// [ksplit][pixel][Cout] float32 slabs, sized for the largest user.
+int alloc_splitk_workspace(ian_handle* h, Plan* pl) {
+  long long need = 0;
+  for (int l = 0; l < L_COUNT; ++l) {
+    TapGemm& g = pl->g[l];
+    if (g.ksplit <= 1) continue;
+    g.ws_slab = (long long)g.n_img * g.Hout * g.Wout * g.Cout;
+    need = std::max(need, g.ws_slab * g.ksplit);
+  }
+  if (need == 0) return IAN_OK;
   float* ws = nullptr;
   int rc = alloc_buf(h, pl, ws, need);
   if (rc != IAN_OK) return rc;
-  for (int l : small) pl->g[l].ws = ws;
+  for (int l = 0; l < L_COUNT; ++l)
+    if (pl->g[l].ksplit > 1) pl->g[l].ws = ws;
   return IAN_OK;
 }
 
@@ -396,12 +404,9 @@ int finish_maps(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(pl->g[l], err, sizeof(err));
     if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
-    if (pl->g[l].ws) {
-      pl->g[l].ksplit = choose_ksplit(pl->g[l]);
-      if (pl->g[l].ksplit == 1) pl->g[l].ws = nullptr;
-    }
+    if (pl->g[l].ksplit == 0) pl->g[l].ksplit = choose_ksplit(pl->g[l]);
   }
-  return IAN_OK;
+  return alloc_splitk_workspace(h, pl);
 }
 
 // decoder of IANv1 (reference IANv1.py:125-201): dense (linear) -> 4 x [deconv, BN, relu] -> RGB-Beta head.  The last deconv
@@ -422,10 +427,9 @@ int build_plan_v1(ian_handle* h, Plan* pl, Plan** out) {
   g[F_DEC_CONV4].act = ACT_RELU; outp(g[F_DEC_CONV4], pl->fh4);
   set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
   g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
-  int rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
-                                           L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4});
-  if (rc != IAN_OK) return rc;
-  rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2,
+  mark_splitk_candidates(pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
+                              L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4});
+  int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2,
                            L_DEC_CONV3, F_DEC_CONV4, F_HEAD});
   if (rc != IAN_OK) return rc;
   *out = pl;
@@ -462,10 +466,9 @@ int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
   // times), written channel-major; the dilated taps are applied afterwards as coalesced shifted reads (head_gather)
   set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
   g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
-  int rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A,
-                                           F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4});
-  if (rc != IAN_OK) return rc;
-  rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
+  mark_splitk_candidates(pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A,
+                              F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4});
+  int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
                                F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD});
   if (rc != IAN_OK) return rc;
   *out = pl;
@@ -482,7 +485,7 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   const bool full = h->model_kind == IAN_MODEL_FULL, v1 = h->model_kind == IAN_MODEL_V1;
   AP(a1, N * 32 * 32 * 128) AP(a2, N * 16 * 16 * 256) AP(a3, N * 8 * 8 * 512) AP(a4, N * 4 * 4 * 1024)
   AP(f1, N * 1024) AP(zp, N * 128)
-  AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(ws_fc1, N * 1024) AB(eps, N * 100)
+  AB(x, N * 3 * 4096) AB(head, N * 256) AB(z, N * 100) AB(xhat, N * 3 * 4096) AB(eps, N * 100)
   if (!full) {
     AP(h0, N * 16384) AP(h1, N * 8 * 8 * 512) AP(h2, N * 16 * 16 * 256) AP(h3, N * 32 * 32 * 128)
   }
@@ -514,7 +517,7 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   g[L_ENC_CONV4].act = ACT_LRELU; g[L_ENC_CONV4].out = pl->a4.p; g[L_ENC_CONV4].out_plane = pl->a4.plane;
   set_io(g[L_ENC_FC1], pl->a4, n, 1, 1, 16384, 1, 1, h->w[L_ENC_FC1], 1, 1); taps_dense(g[L_ENC_FC1]);
   g[L_ENC_FC1].act = has_flow(h) ? ACT_RELU : ACT_ELU;   // IAN.py:118 / IANv1.py:109 use rectify, IAN_simple.py:121 elu
-  g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ws = pl->ws_fc1;
+  g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ksplit = 0;
   set_io(g[L_ENC_HEAD], pl->f1, n, 1, 1, 1024, 1, 1, h->w[L_ENC_HEAD], 1, 1); taps_dense(g[L_ENC_HEAD]);
   g[L_ENC_HEAD].act = ACT_NONE; g[L_ENC_HEAD].out_f32 = pl->head;
   if (full) return build_plan_full(h, pl, out);
@@ -537,21 +540,17 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   g[L_BWD_CONV1].act = ACT_MASK; g[L_BWD_CONV1].mask = pl->h0.p; g[L_BWD_CONV1].out = pl->d0.p; g[L_BWD_CONV1].out_plane = pl->d0.plane;
   g[L_BWD_CONV1].scale_pix_stride = 1024;   // bnorm_dec_fc2 is per FEATURE (pixel, channel)
   set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
-  g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ws = pl->gpad;
+  g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ksplit = 0;
 
-  if ((rc = assign_splitk_workspace(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
-                                            L_DEC_CONV2, L_DEC_CONV3, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1})) != IAN_OK)
-    return rc;
+  mark_splitk_candidates(pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
+                              L_DEC_CONV2, L_DEC_CONV3, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1});
   for (int l = 0; l < F_DEC_FC2; ++l) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
     if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
-    if (g[l].ws) {
-      g[l].ksplit = choose_ksplit(g[l]);
-      if (g[l].ksplit == 1) g[l].ws = nullptr;
-    }
+    if (g[l].ksplit == 0) g[l].ksplit = choose_ksplit(g[l]);
   }
-  // the split-K finalize of dz writes its result in place (ws == out_f32): finalize reads then writes
+  if ((rc = alloc_splitk_workspace(h, pl)) != IAN_OK) return rc;
   {
     char err[256] = {0};
     pl->decout_maps = decout_build_maps(pl->h3.p, pl->h3.plane, n, h->decout_tc_wt, 80 * 128, err, sizeof(err));
@@ -598,6 +597,7 @@ struct ScopedTimer {
 
 int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
+  if (g.ksplit < 1) return fail(h, IAN_ERR_INVALID, "layer %s is not part of this plan", kLayerNames[l]);
   g.passes = h->passes;
   g.sk_ws = h->streamk ? h->sk_ws : nullptr;
   g.sk_flags = h->sk_flags;
@@ -614,8 +614,6 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     LAUNCH_TRY(h, launch_tapgemm_simt(g, st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
   } else {
-    if (g.ksplit > 1)
-      CUDA_TRY(h, cudaMemsetAsync(g.ws, 0, (size_t)g.n_img * g.Hout * g.Wout * g.Cout * sizeof(float), st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
     LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));

@@ -63,10 +63,12 @@ struct TapGemm {
   long long out_plane;
   float* out_f32;
   int Hout, Wout, osh, osw;
-  // split-K (tensor-core path, small-M layers): raw accumulators are atomically added to ws, a
-  // finalize kernel applies the epilogue.
+  // split-K (tensor-core path, small-M layers): K split s stores its raw accumulators to slab s of ws
+  // ([ksplit][pixel][Cout], slab stride ws_slab floats); a finalize kernel adds the slabs in split order and
+  // applies the epilogue -- no atomics, no zero-fill, bit-reproducible.
   int ksplit;
   float* ws;
+  long long ws_slab;
   // MDBLOCK support (reference layers.py:411-416): `res` (output geometry, split planes) is added to the sum
   // before scale/shift; `out_raw` receives the un-normalised sum (the block's residual input x)
   const __nv_bfloat16* res;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
   }
 }
 
-// ws[pix][Cout] raw accumulators -> epilogue -> planes / f32.  One thread per 4 channels.
+// ws[split][pix][Cout] raw accumulators -> sum over splits -> epilogue -> planes / f32.  One thread per 4 channels.
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_constant__ TapGemm g, long long npix) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4 = g.Cout / 4;
@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_const
   const int co = (int)(idx % c4) * 4;
   const int ow = (int)(pix % g.Wout);
   const int oh = (int)((pix / g.Wout) % g.Hout);
-  float4 a = *reinterpret_cast<const float4*>(g.ws + pix * g.Cout + co);
+  const float* wp = g.ws + pix * g.Cout + co;
+  float4 a = __ldcg(reinterpret_cast<const float4*>(wp));
+  for (int k = 1; k < g.ksplit; ++k) {                     // fixed order: bit-reproducible
+    const float4 b = __ldcg(reinterpret_cast<const float4*>(wp + (long long)k * g.ws_slab));
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
   float ar[4] = {a.x, a.y, a.z, a.w};
   __align__(8) __nv_bfloat16 hi4[4], lo4[4];
   __align__(16) float f4[4];

@@ -14,7 +14,7 @@
 //                accumulator so their rounding does not ride on the main sum's exponent).
 //   warps 2..9 : epilogue.  tcgen05.ld both accumulators, add, BatchNorm scale/shift + activation
 //                (or backward scale * ReLU-mask), re-split to bf16 hi/lo planes and store NHWC at
-//                the phase's output stride; or atomically add raw sums for split-K.
+//                the phase's output stride; or store raw sums to this K split's workspace slab.
 // Pipeline: STAGES-deep smem ring with full/empty mbarriers (TMA -> MMA -> tcgen05.commit).
 #include <cuda.h>
 
@@ -390,10 +390,10 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
             }
           }
           if (g.ksplit > 1) {
-            if (valid) {
-              float* wsp = g.ws + pix * g.Cout + co;
+            if (valid) {                                  // this K split's slab; the finalize kernel adds them in order
+              float4* wsp = reinterpret_cast<float4*>(g.ws + (long long)wi.ks * g.ws_slab + pix * g.Cout + co);
 #pragma unroll
-              for (int j = 0; j < CH; ++j) atomicAdd(wsp + j, v[j]);
+              for (int j = 0; j < CH / 4; ++j) __stcg(wsp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
             }
             continue;
           }

@@ -68,7 +68,7 @@ def test_full_reconstruct_and_ordering(full_model, gold, PF):
     zr = fn.full_encode(PF, x[:1], masks)
     assert _zclose(z[:1], zr)
     assert np.abs(xh[:1] - fn.full_decode(PF, z[:1])).max() <= 2e-4
-    assert np.abs(xh - full_model.sample_at(z)).max() <= 2e-4      # same math, different atomic summation order
+    assert np.abs(xh - full_model.sample_at(z)).max() <= 2e-4      # fused call vs two calls
 
 
 def test_full_model_has_no_brush_yet(full_model, npe):
@@ -106,7 +106,7 @@ def test_sample_ian_function_set(full_model, gold, PF):
 
 def test_simple_model_function_set_is_flowless(model, golden):
     x = on.to_tanh(golden["images"][:2].astype(np.float64)).astype(np.float32)
-    assert np.abs(model.Zfn(x) - model.encode_images(x)).max() <= 2e-4     # two runs: atomic split-K summation order
+    assert np.abs(model.Zfn(x) - model.encode_images(x)).max() <= 2e-4     # same math through two entry points
     z = golden["z_rand"][:2]
     assert np.array_equal(model.Z_IAF_fn(z), z)
     assert np.abs(model.sample(z) - model.sample_at(z)).max() <= 5e-5
