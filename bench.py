@@ -383,6 +383,21 @@ def main():
             ts.append(time.perf_counter() - t0)
         lat = {"batch": 1, "median_ms": 1e3 * float(np.median(ts)), "min_ms": 1e3 * float(np.min(ts)),
                "api": "IAN.reconstruct(numpy (1,3,64,64)), synchronous, includes H2D/D2H"}
+        # one NPE paint stroke (NPE.py:199-231): gradient step on Z, re-decode, DELTA/MASK/ERROR blend, 256x256 display
+        z1 = model.encode_images(x1)
+        recon = np.uint8((model.sample_at(z1)[0] + 1.0) * 127.5)
+        err = np.zeros((3, 64, 64), np.float32)
+        frame = np.full((1, 3, 64, 64), 0.25, np.float32)
+        box = [20.0, 20.0, 30.0, 30.0]
+        for _ in range(5):
+            model.paint_stroke(z1, box, frame, recon, err)
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            model.paint_stroke(z1, box, frame, recon, err)
+            ts.append(time.perf_counter() - t0)
+        lat["paint_stroke_median_ms"] = 1e3 * float(np.median(ts))
+        lat["paint_stroke_api"] = "IAN.paint_stroke: one library call per stroke, kernels replayed as one CUDA graph"
 
     # ---- secondary block: full IAN (reference IAN.py graph), BASELINE configs[2] size (batch 512)
     full = None

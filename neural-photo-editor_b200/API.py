@@ -97,6 +97,7 @@ class IAN:
         self.model = {k: base[:-3] + '.' + k for k in keys}
         self.dnn = dnn
         self._lib = _lib.load()
+        self._stream_outs = {}                              # reconstruct_stream's rotating pinned result buffers
         self._h = C.c_void_p()
         rc = self._lib.ian_create(kind, int(device), C.byref(self._h))
         if rc != _lib.IAN_OK:
@@ -131,6 +132,7 @@ class IAN:
         if getattr(self, '_h', None):
             self._lib.ian_destroy(self._h)
             self._h = None
+            self._stream_outs = {}                          # the pinned memory went with the handle
 
     def __del__(self):
         try:
@@ -308,8 +310,9 @@ class IAN:
     def reconstruct_stream(self, batches):
         """Generator over an iterable of (n,3,64,64) float32 batches: yields each reconstruction in order while
         keeping two batches in flight (H2D / compute / D2H of neighbouring batches overlap).  The yielded array
-        is one of two rotating pinned buffers: consume it before advancing the generator twice."""
-        outs, pending = {}, None
+        is one of two rotating pinned buffers owned by the model (allocated on first use per batch shape, reused by
+        later calls): consume it before advancing the generator twice, and run one stream at a time."""
+        outs, pending = self._stream_outs, None              # page-locking costs milliseconds: keep the buffers
         for i, x in enumerate(batches):
             x = _f32(x, 4, 'images')
             key = (i & 1, x.shape)

@@ -161,6 +161,8 @@ struct ian_handle {
   int* sk_flags = nullptr;
   int sk_epoch = 0;
   bool streamk = true;
+  bool graphs = true;          // replay small-batch host calls as CUDA graphs (IAN_GRAPHS=0 turns it off)
+  bool capturing = false;
   bool finalized = false;
   cudaStream_t stream = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined host API
@@ -245,6 +247,10 @@ struct Plan {
   // pipelined host API: double-buffered boundary tensors + events (allocated on first use)
   float *sx[2] = {nullptr, nullptr}, *sz[2] = {nullptr, nullptr}, *sxh[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  // CUDA graphs of the kernel sequences behind the host entry points (small batches only; see run_graphed)
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t key = 0; };
+  enum { G_ENCODE, G_ENCODE_EPS, G_DECODE, G_RECON, G_GRAD, G_EDIT_STEP, G_STROKE, G_COUNT };
+  GraphSlot graph[G_COUNT];
   std::vector<void*> allocs;
 };
 
@@ -569,6 +575,7 @@ void free_plan(Plan* pl) {
   }
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps[l]) tc_free_maps(pl->maps[l]);
   if (pl->decout_maps) decout_free_maps(pl->decout_maps);
+  for (auto& gs : pl->graph) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   delete pl;
 }
 
@@ -599,7 +606,7 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
   if (g.ksplit < 1) return fail(h, IAN_ERR_INVALID, "layer %s is not part of this plan", kLayerNames[l]);
   g.passes = h->passes;
-  g.sk_ws = h->streamk ? h->sk_ws : nullptr;
+  g.sk_ws = (h->streamk && !h->capturing) ? h->sk_ws : nullptr;   // the stream-K epoch is a kernel argument: not replayable
   g.sk_flags = h->sk_flags;
   g.sk_epoch = ++h->sk_epoch;
   ian_handle::Timed tm{};
@@ -1119,6 +1126,47 @@ int for_chunks(ian_handle* h, int n, F&& f) {
   return IAN_OK;
 }
 
+// The interactive calls (NPE: batch 1) are launch-bound: ~20-40 kernels of a few microseconds each.  The kernel
+// sequence of a host entry point depends only on the plan (fixed buffers, fixed tensor maps) and a few scalars, so it is
+// captured once per (plan, entry point, key) and replayed with one cudaGraphLaunch; the H2D/D2H copies of the
+// caller's buffers stay outside the graph.  Large batches are not launch-bound (and may schedule stream-K, whose
+// epoch is a kernel argument): they keep plain launches.
+constexpr int kGraphMaxBatch = 32;
+
+template <typename F>
+int run_graphed(ian_handle* h, Plan* pl, int slot, uint64_t key, cudaStream_t st, F&& body) {
+  if (!h->graphs || h->timing || h->path != IAN_PATH_TC || pl->n > kGraphMaxBatch || st != h->stream || h->gather_dsts)
+    return body();
+  Plan::GraphSlot& gs = pl->graph[slot];
+  key = key * 4 + (uint64_t)(h->passes == 1 ? 1 : 0) + 2;      // +2: a valid key is never 0
+  if (gs.exec && gs.key != key) {
+    cudaGraphExecDestroy(gs.exec);
+    gs.exec = nullptr;
+  }
+  if (!gs.exec) {
+    const int64_t l0 = h->launches;
+    CUDA_TRY(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    h->capturing = true;
+    const int r = body();
+    h->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    gs.launches = h->launches - l0;
+    h->launches = l0;
+    if (r != IAN_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) return fail(h, IAN_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(&gs.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { gs.exec = nullptr; return fail(h, IAN_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+    gs.key = key;
+  }
+  CUDA_TRY(h, cudaGraphLaunch(gs.exec, st));
+  h->launches += gs.launches;
+  return IAN_OK;
+}
+
+inline uint64_t float_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
 }  // namespace
 
 // ================================================================================================
@@ -1152,6 +1200,7 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
   if (const char* c = getenv("IAN_STREAMK")) h->streamk = atoi(c) != 0;
+  if (const char* c = getenv("IAN_GRAPHS")) h->graphs = atoi(c) != 0;
   *out = h;
   return IAN_OK;
 }
@@ -1300,7 +1349,8 @@ int ian_encode_host(ian_handle* h, const float* x, int n, const float* eps, floa
   rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
     CUDA_TRY(h, cudaMemcpyAsync(pl->x, x + (size_t)off * 12288, (size_t)cn * 12288 * 4, cudaMemcpyHostToDevice, st));
     if (eps) CUDA_TRY(h, cudaMemcpyAsync(pl->eps, eps + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
-    int r = run_encode(h, pl, pl->x, eps ? pl->eps : nullptr, pl->z, st);
+    int r = run_graphed(h, pl, eps ? Plan::G_ENCODE_EPS : Plan::G_ENCODE, 0, st,
+                        [&] { return run_encode(h, pl, pl->x, eps ? pl->eps : nullptr, pl->z, st); });
     if (r != IAN_OK) return r;
     CUDA_TRY(h, cudaMemcpyAsync(z + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
     return (int)IAN_OK;
@@ -1328,7 +1378,7 @@ int ian_decode_host(ian_handle* h, const float* z, int n, float* x) {
   cudaStream_t st = h->stream;
   rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
     CUDA_TRY(h, cudaMemcpyAsync(pl->z, z + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
-    int r = run_decode(h, pl, pl->z, pl->xhat, st);
+    int r = run_graphed(h, pl, Plan::G_DECODE, 0, st, [&] { return run_decode(h, pl, pl->z, pl->xhat, st); });
     if (r != IAN_OK) return r;
     CUDA_TRY(h, cudaMemcpyAsync(x + (size_t)off * 12288, pl->xhat, (size_t)cn * 12288 * 4, cudaMemcpyDeviceToHost, st));
     return (int)IAN_OK;
@@ -1358,9 +1408,11 @@ int ian_reconstruct_host(ian_handle* h, const float* x, int n, float* z_out, flo
   cudaStream_t st = h->stream;
   rc = for_chunks(h, n, [&](Plan* pl, int off, int cn) {
     CUDA_TRY(h, cudaMemcpyAsync(pl->x, x + (size_t)off * 12288, (size_t)cn * 12288 * 4, cudaMemcpyHostToDevice, st));
-    int r = run_encode(h, pl, pl->x, nullptr, pl->z, st);
+    int r = run_graphed(h, pl, Plan::G_RECON, 0, st, [&] {
+      int q = run_encode(h, pl, pl->x, nullptr, pl->z, st);
+      return q != IAN_OK ? q : run_decode_from_planes(h, pl, pl->xhat, st);
+    });
     if (r != IAN_OK) return r;
-    if ((r = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return r;
     if (z_out) CUDA_TRY(h, cudaMemcpyAsync(z_out + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(x_hat + (size_t)off * 12288, pl->xhat, (size_t)cn * 12288 * 4, cudaMemcpyDeviceToHost, st));
     return (int)IAN_OK;
@@ -1403,10 +1455,14 @@ int ian_grad_host(ian_handle* h, const float* z, const int32_t* boxes, const flo
     CUDA_TRY(h, cudaMemcpyAsync(pl->z, z + (size_t)off * 100, (size_t)cn * 400, cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpyAsync(pl->boxes, boxes + (size_t)off * 4, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
     if (target) CUDA_TRY(h, cudaMemcpyAsync(pl->target, target + off * tstride, cn * tstride * 4, cudaMemcpyHostToDevice, st));
-    LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
-    int r = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+    int r = run_graphed(h, pl, Plan::G_GRAD, (target ? 1 : 0) + (target_is_frame ? 2 : 0), st, [&] {
+      LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
+      int q = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+      if (q != IAN_OK) return q;
+      LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, 0.f, pl->z /*reuse as g staging*/, nullptr, nullptr, 0, cn, st));
+      return (int)IAN_OK;
+    });
     if (r != IAN_OK) return r;
-    LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, 0.f, pl->z /*reuse as g staging*/, nullptr, nullptr, 0, cn, st));
     CUDA_TRY(h, cudaMemcpyAsync(g + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
     return (int)IAN_OK;
   });
@@ -1453,10 +1509,15 @@ int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const floa
     CUDA_TRY(h, cudaMemcpyAsync(pl->boxes, boxes + (size_t)off * 4, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
     if (target) CUDA_TRY(h, cudaMemcpyAsync(pl->target, target + off * tstride, cn * tstride * 4, cudaMemcpyHostToDevice, st));
     LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, cn, st));
-    for (int s = 0; s < n_steps; ++s) {
-      int r = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+    const uint64_t key = float_bits(weight) * 4 + (target ? 1 : 0) + (target_is_frame ? 2 : 0);
+    for (int s = 0; s < n_steps; ++s) {                    // one graph = one paint step, replayed n_steps times
+      int r = run_graphed(h, pl, Plan::G_EDIT_STEP, key, st, [&] {
+        int q = run_grad_core(h, pl, pl->boxes, target ? pl->target : nullptr, target_is_frame, st);
+        if (q != IAN_OK) return q;
+        LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, cn, st));
+        return (int)IAN_OK;
+      });
       if (r != IAN_OK) return r;
-      LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, cn, st));
     }
     CUDA_TRY(h, cudaMemcpyAsync(z + (size_t)off * 100, pl->z, (size_t)cn * 400, cudaMemcpyDeviceToHost, st));
     return (int)IAN_OK;
@@ -1677,11 +1738,16 @@ int ian_paint_stroke_host(ian_handle* h, float* z, const int32_t* box, const flo
   CUDA_TRY(h, cudaMemcpyAsync(pl->target, rgb_frame, 12288 * 4, cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaMemcpyAsync(d_recon, recon_u8, 12288, cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaMemcpyAsync(d_error, error, 12288 * 4, cudaMemcpyHostToDevice, st));
-  LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, 1, st));
-  if ((rc = run_grad_core(h, pl, pl->boxes, pl->target, 1, st)) != IAN_OK) return rc;           // NPE.py:205
-  LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, 1, st));  // :206-209
-  if ((rc = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return rc;                   // NPE.py:218 sample_at
-  LAUNCH_TRY(h, launch_npe_blend(pl->xhat, d_recon, d_error, d_im, d_disp, st));                  // NPE.py:218-231
+  rc = run_graphed(h, pl, Plan::G_STROKE, float_bits(weight), st, [&] {
+    LAUNCH_TRY(h, launch_z_to_planes(pl->z, pl->zp.p, pl->zp.plane, 1, st));
+    int q = run_grad_core(h, pl, pl->boxes, pl->target, 1, st);                                    // NPE.py:205
+    if (q != IAN_OK) return q;
+    LAUNCH_TRY(h, launch_brush_update(pl->gpad, pl->boxes, weight, nullptr, pl->z, pl->zp.p, pl->zp.plane, 1, st));  // :206-209
+    if ((q = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return q;                     // NPE.py:218 sample_at
+    LAUNCH_TRY(h, launch_npe_blend(pl->xhat, d_recon, d_error, d_im, d_disp, st));                  // NPE.py:218-231
+    return (int)IAN_OK;
+  });
+  if (rc != IAN_OK) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(z, pl->z, 400, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaMemcpyAsync(im_u8, d_im, 12288, cudaMemcpyDeviceToHost, st));
   if (display_u8) CUDA_TRY(h, cudaMemcpyAsync(display_u8, d_disp, 256 * 256 * 3, cudaMemcpyDeviceToHost, st));

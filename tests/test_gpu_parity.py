@@ -200,6 +200,47 @@ def test_reruns_are_bit_identical(model):
             assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
 
 
+def test_graph_replay_equals_plain_launches(model, weights, golden, monkeypatch):
+    """Small-batch host calls replay a captured CUDA graph; it must be the same kernels on the same buffers: results
+    equal those of a handle with graphs off (IAN_GRAPHS=0) bit for bit, on the capture call and on the replays, and a
+    changed scalar (the step weight) re-captures."""
+    import importlib
+    pkg = importlib.import_module("neural-photo-editor_b200")
+    monkeypatch.setenv("IAN_GRAPHS", "0")
+    plain = pkg.IAN("IAN_simple.py", True, weights=weights)
+    monkeypatch.delenv("IAN_GRAPHS")
+    rng = np.random.default_rng(33)
+    for n in (1, 6):
+        x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
+        z = rng.standard_normal((n, 100)).astype(np.float32)
+        boxes = np.tile(np.array([[10, 12, 30, 44]], np.int32), (n, 1))
+        rgb = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        l0 = model.launch_count()
+        for rep in range(3):                                 # rep 0 may capture, 1-2 replay
+            xa, za = model.reconstruct(x, return_z=True)
+            xb, zb = plain.reconstruct(x, return_z=True)
+            assert np.array_equal(xa, xb) and np.array_equal(za, zb)
+            assert np.array_equal(model.encode_images(x), plain.encode_images(x))
+            assert np.array_equal(model.sample_at(z), plain.sample_at(z))
+            assert np.array_equal(model.grad(z, boxes, rgb), plain.grad(z, boxes, rgb))
+            assert np.array_equal(model.grad(z, boxes), plain.grad(z, boxes))            # other target kind: own key
+            for w in (0.05, 0.02):
+                assert np.array_equal(model.edit_steps(z, boxes, rgb, n_steps=4, weight=w),
+                                      plain.edit_steps(z, boxes, rgb, n_steps=4, weight=w))
+        assert model.launch_count() > l0                     # replays are counted kernel by kernel
+    x1 = on.to_tanh(golden["images"][:1].astype(np.float64)).astype(np.float32)
+    z0 = model.encode_images(x1)
+    recon = np.uint8(on.from_tanh(model.sample_at(z0)[0]))
+    err = np.zeros((3, 64, 64), np.float32)
+    frame = np.full((1, 3, 64, 64), 0.3, np.float32)
+    for rep in range(2):
+        a = model.paint_stroke(z0, [8.0, 8.0, 24.0, 24.0], frame, recon, err, weight=0.05)
+        b = plain.paint_stroke(z0, [8.0, 8.0, 24.0, 24.0], frame, recon, err, weight=0.05)
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    plain.close()
+
+
 def test_paint_stroke_matches_npe_paint(model, golden, weights):
     """one stroke = one call: gradient step, re-decode and NPE's DELTA/MASK/ERROR blend (NPE.py:199-231)."""
     x = on.to_tanh(golden["images"][:1].astype(np.float64)).astype(np.float32)
