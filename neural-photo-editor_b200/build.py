@@ -35,5 +35,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+C_HOST_SRC = os.path.join(HERE, "..", "examples", "c_host", "ian_cli.c")
+C_HOST_BIN = os.path.join(HERE, "..", "examples", "c_host", "ian_cli")
+
+
+def build_c_host(force: bool = False) -> str:
+    """the plain-C host program over the C-ABI (examples/c_host): strict C99 against include/ian_b200.h, linked to
+    the in-tree library with an $ORIGIN-relative rpath so it runs from the snapshot on the GPU box."""
+    lib = build()
+    deps = [C_HOST_SRC, os.path.join(HERE, "..", "include", "ian_b200.h"), lib]
+    if not force and os.path.exists(C_HOST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(C_HOST_BIN) for d in deps):
+        return C_HOST_BIN
+    cmd = [os.environ.get("CC", "gcc"), "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic",
+           "-I", os.path.join(HERE, "..", "include"), C_HOST_SRC, "-o", C_HOST_BIN,
+           "-L", HERE, "-lian_b200", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE)]
+    subprocess.run(cmd, check=True)
+    return C_HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_c_host(force="--force" in sys.argv))

@@ -75,3 +75,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def _c_host():
+    import importlib
+    return importlib.import_module("neural-photo-editor_b200.build").build_c_host()
+
+
+def test_c_host_program_links_every_entry_point():
+    """examples/c_host/ian_cli.c is strict C99 (-Wall -Wextra -Werror -pedantic) against include/ian_b200.h: the header
+    is a C header, and taking every entry point by address makes a missing export a link error."""
+    import subprocess
+    exe = _c_host()
+    out = subprocess.run([exe, "--symbols"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split()[0] == str(len(_declared_symbols()))
+    src = open(os.path.join(ROOT, "examples", "c_host", "ian_cli.c")).read()
+    for name in _declared_symbols():
+        assert "(anyfn)%s," % name in src or "(anyfn)%s}" % name in src, name
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_c_host_program_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    out = subprocess.run([_c_host(), str(tmp_path / "w.bin"), str(tmp_path / "x.f32"), "1", str(tmp_path / "o.f32")],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "no CPU path" in out.stderr
