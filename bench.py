@@ -303,9 +303,9 @@ def main():
     roofline = {"bound": "tensor", "kernel": "tapgemm_tc_kernel", "achieved": achieved, "peak": peak_fp32_equiv,
                 "unit": "TFLOP/s", "frac": achieved / peak_fp32_equiv,
                 # dram__bytes_read+write summed over the 9 tap-GEMM launches of one step, from the ncu --set full
-                # capture of this same command (profiles/r1_ncu_tc_kernels_full_summary.csv: 736.5 MB read + 203.2 MB
+                # capture of this same command (profiles/r1_ncu_tc_kernels_full_summary.csv: 753.0 MB read + 206.2 MB
                 # written); algorithmic bytes of those launches are 943 MB (573 MB operands read once + 370 MB outputs)
-                "traffic": 939.7e6 if BATCH == 256 else None, "traffic_unit": "bytes per step (all tap-GEMM launches)",
+                "traffic": 959.2e6 if BATCH == 256 else None, "traffic_unit": "bytes per step (all tap-GEMM launches)",
                 "peak_note": "%s bf16_tflops_sustained (%.1f) / 3: fp32 parity is reached by a 3-pass bf16 split, so each "
                              "algorithmic MAC costs 3 tensor-core MACs" % (pk["src"], pk["bf16_tflops_sustained"]),
                 "tensor_executed_tflops": 3 * achieved, "kernel_ms_per_step": tg_ms,
