@@ -282,7 +282,8 @@ __global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_
 
 // ------------------------------------------------------------------------------------------------
 // full IAN latent: z = (z0 - MADE_mu(z0)) / exp(MADE_ls(z0))     (reference IAN.py:126-128; layers.py:641-853)
-//   MADE(z) = relu(z (W0*M0) + b0) (W1*M1) + b1 + z (Wd*Md) + bd ; the masks are pre-multiplied on the host
+//   MADE(z) = core(in(z)),  in(v) = relu(v (W0*M0) + b0),  core(u) = in(u) (W1*M1) + b1 + u (Wd*Md) + bd
+//   (the input MaskedLayer runs twice: see below); the masks are pre-multiplied on the host
 // mw: [2 nets][3 matrices: input, output_W, output_D][100][100] fp32 (in,out); mb: [2][3][100].
 // one block per sample, 128 threads.
 // ------------------------------------------------------------------------------------------------
@@ -290,16 +291,29 @@ __global__ void __launch_bounds__(128) made_iaf_kernel(const float* __restrict__
                                                        const float* __restrict__ mb, float* __restrict__ z,
                                                        __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
   __shared__ float zs[100];
+  __shared__ float us[2][100];
   __shared__ float hs[2][100];
   const int k = blockIdx.x, j = threadIdx.x;
   if (j < 100) zs[j] = z0[k * 100 + j];
   __syncthreads();
+  // u = relu(z W0 + b0): the `<name>_input` MaskedLayer.  MADE.__init__ (layers.py:769) overwrites Layer.input_layer
+  // with it, so inside the reference graph the MADE layer is fed u, not z, and applies its whole stack to u.
   if (j < 100) {
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
       const float* W0 = mw + (net * 3 + 0) * 10000;
       float a = mb[(net * 3 + 0) * 100 + j];
       for (int i = 0; i < 100; ++i) a = fmaf(zs[i], W0[i * 100 + j], a);
+      us[net][j] = 0.5f * (a + fabsf(a));
+    }
+  }
+  __syncthreads();
+  if (j < 100) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      const float* W0 = mw + (net * 3 + 0) * 10000;
+      float a = mb[(net * 3 + 0) * 100 + j];
+      for (int i = 0; i < 100; ++i) a = fmaf(us[net][i], W0[i * 100 + j], a);
       hs[net][j] = 0.5f * (a + fabsf(a));
     }
   }
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(128) made_iaf_kernel(const float* __restrict__
       float a1 = 0.f, a2 = 0.f;
       for (int i = 0; i < 100; ++i) {
         a1 = fmaf(hs[net][i], W1[i * 100 + j], a1);
-        a2 = fmaf(zs[i], Wd[i * 100 + j], a2);
+        a2 = fmaf(us[net][i], Wd[i * 100 + j], a2);
       }
       o[net] = a + a1 + a2;
     }

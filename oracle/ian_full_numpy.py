@@ -44,14 +44,31 @@ def made_masks(ordering):
     return M0, M1, Md
 
 
-def made_forward(P, name, z, masks):
-    """MADE.get_output_for (layers.py:817-818): relu(z(W0*M0)+b0)(W1*M1)+b1 + z(Wd*Md)+bd
-    (MaskedLayer layers.py:666-674, DIML 699-707, ESL at 810)."""
+def made_core(P, name, u, masks):
+    """MADE.get_output_for(u) (layers.py:817-818) = get_output(final_layer, {self.z: u}):
+    relu(u(W0*M0)+b0)(W1*M1)+b1 + u(Wd*Md)+bd   (MaskedLayer layers.py:666-674, DIML 699-707, ESL at 810)."""
     M0, M1, Md = [np.asarray(m, F64) for m in masks]
-    z = np.asarray(z, F64)
-    h = on.rectify(z @ (np.asarray(P[name + "_input.W"], F64) * M0) + np.asarray(P[name + "_input.b"], F64))
+    u = np.asarray(u, F64)
+    h = made_input_layer(P, name, u, masks)
     out = h @ (np.asarray(P[name + "_output_W.W"], F64) * M1) + np.asarray(P[name + "_output_W.b"], F64)
-    return out + z @ (np.asarray(P[name + "_output_D.W"], F64) * Md) + np.asarray(P[name + "_output_D.b"], F64)
+    return out + u @ (np.asarray(P[name + "_output_D.W"], F64) * Md) + np.asarray(P[name + "_output_D.b"], F64)
+
+
+def made_input_layer(P, name, z, masks):
+    """the MaskedLayer `<name>_input`: relu(z(W0*M0)+b0)  (layers.py:769-775)."""
+    M0 = np.asarray(masks[0], F64)
+    return on.rectify(np.asarray(z, F64) @ (np.asarray(P[name + "_input.W"], F64) * M0) + np.asarray(P[name + "_input.b"], F64))
+
+
+def made_forward(P, name, z, masks):
+    """What the MADE layer computes INSIDE THE REFERENCE GRAPH.  MADE.__init__ stores its first MaskedLayer in
+    `self.input_layer` (layers.py:769) -- the very attribute lasagne.layers.Layer uses to record the layer's input
+    (set to `z` by Layer.__init__ at layers.py:738) and that get_all_layers / get_output follow.  So, wired into
+    IAN.py:127 / IANv1.py:123, the MADE layer is fed the OUTPUT of `<name>_input` rather than z, and then applies its
+    whole stack (input layer included) to that:   made_core(made_input_layer(z)).
+    Found by executing the reference's files (tests/golden/make_golden_ref.py); made_core alone is what a reading
+    of MADE.get_output_for suggests and is NOT what API.IAN / sample_IAN.py evaluate."""
+    return made_core(P, name, made_input_layer(P, name, z, masks), masks)
 
 
 def iaf(z, mu, ls):

@@ -160,9 +160,12 @@ def mdblock(P, name, x, scales, mdcl_fn=mdcl):
 
 
 def made(P, name, z, masks):
+    """the MADE layer as wired in the reference graph: its `<name>_input` MaskedLayer runs twice, because
+    MADE.__init__ overwrites Layer.input_layer with it (layers.py:769; see oracle/ian_full_numpy.made_forward)."""
     M0, M1, Md = masks
-    h = _relu(z @ (P[name + "_input.W"] * M0) + P[name + "_input.b"])
-    return h @ (P[name + "_output_W.W"] * M1) + P[name + "_output_W.b"] + z @ (P[name + "_output_D.W"] * Md) + P[name + "_output_D.b"]
+    u = _relu(z @ (P[name + "_input.W"] * M0) + P[name + "_input.b"])
+    h = _relu(u @ (P[name + "_input.W"] * M0) + P[name + "_input.b"])
+    return h @ (P[name + "_output_W.W"] * M1) + P[name + "_output_W.b"] + u @ (P[name + "_output_D.W"] * Md) + P[name + "_output_D.b"]
 
 
 def full_encode_mu_ls(P, x):

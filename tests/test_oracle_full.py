@@ -36,17 +36,36 @@ def test_made_mask_structure():
 
 
 def test_made_is_autoregressive(PF):
-    """output j of a MADE depends only on inputs i with ordering[i] < ordering[j]."""
+    """the MADE stack itself (made_core): output j depends only on inputs i with ordering[i] < ordering[j]."""
+    o = fn.made_ordering()
+    masks = fn.made_masks(o)
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((1, 100))
+    base = fn.made_core(PF, "l_IAF_mu", z, masks)
+    i = int(np.where(o == 50)[0][0])
+    z2 = z.copy()
+    z2[0, i] += 1.0
+    d = np.abs(fn.made_core(PF, "l_IAF_mu", z2, masks) - base)[0]
+    assert np.all(d[o <= 50] == 0) and np.any(d[o > 50] > 0)
+
+
+def test_made_as_wired_in_the_reference_graph(PF):
+    """as wired (layers.py:769: the MADE layer is fed its own input MaskedLayer, see made_forward) the layer's output is
+    made_core(relu(z W0*M0 + b0)); with one hidden layer of all-ones connectivity M0 keeps only the input whose
+    ordering is 0, so the whole flow reads a single latent -- what the executed reference shows, restated here."""
     o = fn.made_ordering()
     masks = fn.made_masks(o)
     rng = np.random.default_rng(0)
     z = rng.standard_normal((1, 100))
     base = fn.made_forward(PF, "l_IAF_mu", z, masks)
-    i = int(np.where(o == 50)[0][0])
+    assert np.abs(base - fn.made_core(PF, "l_IAF_mu", fn.made_input_layer(PF, "l_IAF_mu", z, masks), masks)).max() == 0
+    i0 = int(np.where(o == 0)[0][0])
     z2 = z.copy()
-    z2[0, i] += 1.0
-    d = np.abs(fn.made_forward(PF, "l_IAF_mu", z2, masks) - base)[0]
-    assert np.all(d[o <= 50] == 0) and np.any(d[o > 50] > 0)
+    z2[0, np.arange(100) != i0] += 1.0
+    assert np.abs(fn.made_forward(PF, "l_IAF_mu", z2, masks) - base).max() == 0
+    z3 = z.copy()
+    z3[0, i0] += 1.0
+    assert np.abs(fn.made_forward(PF, "l_IAF_mu", z3, masks) - base).max() > 0
 
 
 def test_mdcl_equals_composite_kernel(PF):
