@@ -2,8 +2,10 @@
 graph (reference IAN.py:67-228) and its custom layers (reference layers.py: MDCL 207-258, beta_layer 397-408,
 MDBLOCK 411-416, IAFLayer 641-650, MaskedLayer/DIML/MADE 653-853; mask_generator.py:15-103).
 
-PARITY UNPINNED (see oracle/ian_numpy.py): no Theano/Lasagne here, no golden vectors in the reference.
-Third-party semantics are the named assumptions of SURVEY.md Appendix C/D; in particular
+PARITY: pinned to the executed reference (see the header of oracle/ian_numpy.py): IANv1.get_model() and
+IAN.get_model() run unmodified on oracle/refshim and this file matches their outputs to 1e-11
+(tests/golden/ref_exec_v1.npz, ref_exec_full.npz; tests/test_reference_exec.py).
+Third-party semantics restated underneath are the named assumptions of SURVEY.md Appendix C/D; in particular
   C.1  BN(incoming) inside MDBLOCK deletes the preceding DeconvLayer's bias (layers.py:413),
   C.6  DilatedConv2DLayer on a PadLayer(s) input = correlation with taps at (i-1)*s,
   D    MADE masks depend only on `ordering`; ordering = one legacy-RandomState permutation (seed 1234 stream).

@@ -1,6 +1,6 @@
 """CPU ORACLE (test infrastructure, NOT product code) -- independent float32 torch-CPU restatement.
 
-PARITY UNPINNED (see oracle/ian_numpy.py header).  Written against torch.nn.functional so that it
+PARITY: pinned through oracle/ian_numpy.py, which matches the executed reference (see its header).  Written against torch.nn.functional so that it
 shares no arithmetic code with the float64 definitional version; the two must agree before either
 is trusted (tests/test_oracle.py).  Also the timed CPU baseline of bench.py ("CPU restatement of the
 reference graph, N cores" -- never "Theano").
