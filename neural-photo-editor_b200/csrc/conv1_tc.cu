@@ -31,7 +31,7 @@ constexpr int kAStage = 2 * 2 * kChunkPlane;       // 2 K chunks x (hi|lo): 64 K
 constexpr int kBBytes = 2 * 2 * kChunkPlane;       // weights: 2 K chunks x (hi|lo) x 128 rows: 64 KB
 constexpr int kPatchRows = 11, kPatchCols = 68;
 constexpr int kPatchFloats = 3 * kPatchRows * kPatchCols;
-constexpr int kSmemBytes = 1024 + 2 * kAStage + kBBytes + 2 * kPatchFloats * 4 + 256;
+constexpr int kSmemBytes = 1024 + 2 * kAStage + kBBytes + 2 * kPatchFloats * 4 + 256 + 512;   // + barriers + staged bias
 constexpr int kTilesPerImage = 8;                  // 32 output rows / 4
 
 // one 16-byte unit (8 consecutive k) of row m: values -> bf16 hi|lo -> swizzled position in both planes
@@ -84,6 +84,8 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
   auto tempty_bar = [&](int b) { return bar_base + 8u * (6 + b); };
   const uint32_t b_bar = bar_base + 64u, tmem_slot = bar_base + 72u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_al + (tmem_slot - smem_base));
+  float* bias_s = reinterpret_cast<float*>(smem_al + (bar_base + 256u - smem_base));   // 128 floats, 16-byte aligned
+  if (threadIdx.x < 128) bias_s[threadIdx.x] = __ldg(bias + threadIdx.x);   // the epilogue reads it 2048 times per thread
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = n_img * kTilesPerImage;
@@ -152,24 +154,34 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
       const uint32_t lane_addr = tmem_base + s * 256 + ((uint32_t)(lg * 32) << 16);
       mbar_wait(tfull_bar(s), use & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 16) {
-        const int cb = half * 64 + cc;
-        uint32_t vm[16], vc[16];
-        __syncwarp();
-        tmem_ld16(lane_addr + cb, vm);
-        tmem_ld16(lane_addr + 128 + cb, vc);
+      // software-pipelined drain: the TMEM loads of chunk k+1 are in flight while chunk k is converted and stored
+      uint32_t vm[2][16], vc[2][16];
+      __syncwarp();
+      tmem_ld16(lane_addr + half * 64, vm[0]);
+      tmem_ld16(lane_addr + 128 + half * 64, vc[0]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int cb = half * 64 + 16 * k;
         tmem_ld_wait();
-        if (cc == 48) {
+        if (k < 3) {
+          __syncwarp();
+          tmem_ld16(lane_addr + cb + 16, vm[(k + 1) & 1]);
+          tmem_ld16(lane_addr + 128 + cb + 16, vc[(k + 1) & 1]);
+        } else {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(s));
         }
+        const uint32_t* am = vm[k & 1];
+        const uint32_t* ac = vc[k & 1];
         __align__(16) __nv_bfloat162 hi[8], lo[8];
+        __align__(16) float bv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(bv)[j] = reinterpret_cast<const float4*>(bias_s + cb)[j];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float v0 = __uint_as_float(vm[2 * j]) + __uint_as_float(vc[2 * j]) + __ldg(bias + cb + 2 * j);
-          float v1 = __uint_as_float(vm[2 * j + 1]) + __uint_as_float(vc[2 * j + 1]) + __ldg(bias + cb + 2 * j + 1);
+          float v0 = __uint_as_float(am[2 * j]) + __uint_as_float(ac[2 * j]) + bv[2 * j];
+          float v1 = __uint_as_float(am[2 * j + 1]) + __uint_as_float(ac[2 * j + 1]) + bv[2 * j + 1];
           v0 = fmaf(0.4f, fabsf(v0), 0.6f * v0);
           v1 = fmaf(0.4f, fabsf(v1), 0.6f * v1);
           hi[j] = __floats2bfloat162_rn(v0, v1);
