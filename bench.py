@@ -309,7 +309,11 @@ def main():
                 "peak_note": "%s bf16_tflops_sustained (%.1f) / 3: fp32 parity is reached by a 3-pass bf16 split, so each "
                              "algorithmic MAC costs 3 tensor-core MACs" % (pk["src"], pk["bf16_tflops_sustained"]),
                 "tensor_executed_tflops": 3 * achieved, "kernel_ms_per_step": tg_ms,
-                "kernel_share_of_step": tg_ms / (ms / args.steps),
+                # share among the kernels event-timed in this same pass (tap-GEMMs + enc_conv1 + dec_out); the ncu launch
+                # list of this command (profiles/r1_ncu_launches_bench_steps2.csv) gives 0.92 with the three tiny
+                # finalize/sample kernels also in the denominator
+                "kernel_share_of_step": tg_ms / (tg_ms + sum(v for v in edge_ms.values() if v > 0)),
+                "kernel_ms_vs_untimed_step": tg_ms / (ms / args.steps),
                 "layer_ms": {k: round(v, 4) for k, v in layer_ms.items()},
                 "edge_kernel_ms": {k: round(v, 4) for k, v in edge_ms.items()}}
 
