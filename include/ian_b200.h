@@ -18,6 +18,11 @@
  *     (the numpy-in / numpy-out semantics of the reference's theano.function calls).
  *   - a handle is bound to one device and is not thread-safe (API.IAN is single-threaded: NPE.py calls
  *     it from the Tk main loop).
+ *   - results are reproducible: a call repeated with the same batch size returns the same bits (split-K and
+ *     stream-K partial sums are added in a fixed order; there are no atomics on the path).
+ *   - environment, read by ian_create: IAN_CHUNK=<n> images per internal chunk (default 512); IAN_PATH=simt selects
+ *     the FFMA verification kernels; IAN_STREAMK=0 disables stream-K scheduling; IAN_GRAPHS=0 disables the CUDA-graph
+ *     replay that *_host calls with <= 32 images use.
  */
 #ifndef IAN_B200_H_
 #define IAN_B200_H_
