@@ -15,6 +15,7 @@ central differences of the reference forward in float64.
 
 The GPU box has no /root/reference: tests read only the committed .npz files.
 """
+import json
 import logging
 import os
 import sys
@@ -41,6 +42,12 @@ def _stage(config, weights):
     os.symlink(os.path.join(REF, config), link)
     np.savez(os.path.join(WORK, config[:-3] + '.npz'), **weights)
     return link
+
+
+def _cfg_json(cfg):
+    """the config module's `cfg` dict (API.py:18), JSON with stringified keys"""
+    norm = lambda v: {str(k): norm(x) for k, x in v.items()} if isinstance(v, dict) else (list(v) if isinstance(v, tuple) else v)
+    return np.array(json.dumps(norm(cfg), sort_keys=True))
 
 
 def _loader_params(model):
@@ -76,6 +83,7 @@ def simple():
         print(tag, 'forward done in %.1f s' % (time.time() - t0), flush=True)
         if dnn:
             names = _loader_params(m.model)
+            out['cfg_json'] = _cfg_json(m.cfg)
             out['param_names'] = np.array([n for n, _ in names])
             out['param_shapes'] = np.array([' '.join(map(str, s)) for _, s in names])
             b = [int(v) for v in gold['boxes'][0]]
@@ -107,7 +115,8 @@ def flow_model(which):
     gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'ian_%s_golden.npz' % which))   # inputs only
     P = (ow.make_v1_weights if which == 'v1' else ow.make_full_weights)(int(gold['weight_seed']))
     link = _stage(config, P)
-    model = imp.load_source('config', link).get_model()
+    config_module = imp.load_source('config', link)
+    model = config_module.get_model()
     params = list(set(lasagne.layers.get_all_params(model['l_out'], trainable=True) +
                       lasagne.layers.get_all_params(model['l_discrim'], trainable=True) +
                       [x for x in lasagne.layers.get_all_params(model['l_out']) + lasagne.layers.get_all_params(model['l_discrim'])
@@ -128,7 +137,8 @@ def flow_model(which):
     }
     x = on.to_tanh(gold['images'].astype(np.float64)).astype(np.float32)
     names = sorted((p.name, tuple(p.get_value().shape)) for p in params)
-    out = {'param_names': np.array([n for n, _ in names]),
+    out = {'cfg_json': _cfg_json(config_module.cfg),
+           'param_names': np.array([n for n, _ in names]),
            'param_shapes': np.array([' '.join(map(str, s)) for _, s in names]),
            'ordering_mu': model['l_IAF_mu'].mask_generator.ordering.get_value(),
            'ordering_ls': model['l_IAF_ls'].mask_generator.ordering.get_value(),

@@ -112,3 +112,19 @@ def test_fixture_regenerates_from_the_reference(tmp_path):
     assert sorted(committed.files) == sorted(fresh.files)
     for k in committed.files:
         assert np.array_equal(committed[k], fresh[k]), k
+
+
+def test_product_cfg_dicts_equal_the_reference_config_modules(npe):
+    """API.IAN.cfg (reference API.py:18 reads it from the config module; NPE and sample_IAN.py read cfg['num_latents'])"""
+    import json
+    api = __import__(npe.__name__ + ".API", fromlist=["API"])
+    norm = lambda v: {str(k): norm(x) for k, x in v.items()} if isinstance(v, dict) else (list(v) if isinstance(v, tuple) else v)
+    for fixture, mine in (("ref_exec_v1.npz", dict(api._FULL_CFG, max_epochs=150)), ("ref_exec_full.npz", api._FULL_CFG),
+                          ("ref_exec_simple.npz", api._SIMPLE_CFG)):
+        ref = json.loads(str(_load(fixture)["cfg_json"]))
+        if fixture == "ref_exec_v1.npz":
+            ref_wo, mine_wo = dict(ref), norm(mine)
+            mine_wo.pop("ortho", None)                      # IANv1.py has no 'ortho' entry (API.py of the product pops it too)
+            assert ref_wo == mine_wo
+        else:
+            assert ref == norm(mine), fixture
