@@ -84,6 +84,7 @@ def simple():
         if dnn:
             names = _loader_params(m.model)
             out['cfg_json'] = _cfg_json(m.cfg)
+            out['model_keys'] = np.array(sorted(m.model.keys()))
             out['param_names'] = np.array([n for n, _ in names])
             out['param_shapes'] = np.array([' '.join(map(str, s)) for _, s in names])
             b = [int(v) for v in gold['boxes'][0]]
@@ -138,6 +139,7 @@ def flow_model(which):
     x = on.to_tanh(gold['images'].astype(np.float64)).astype(np.float32)
     names = sorted((p.name, tuple(p.get_value().shape)) for p in params)
     out = {'cfg_json': _cfg_json(config_module.cfg),
+           'model_keys': np.array(sorted(model.keys())),
            'param_names': np.array([n for n, _ in names]),
            'param_shapes': np.array([' '.join(map(str, s)) for _, s in names]),
            'ordering_mu': model['l_IAF_mu'].mask_generator.ordering.get_value(),

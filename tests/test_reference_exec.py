@@ -122,6 +122,8 @@ def test_product_cfg_dicts_equal_the_reference_config_modules(npe):
     for fixture, mine in (("ref_exec_v1.npz", dict(api._FULL_CFG, max_epochs=150)), ("ref_exec_full.npz", api._FULL_CFG),
                           ("ref_exec_simple.npz", api._SIMPLE_CFG)):
         ref = json.loads(str(_load(fixture)["cfg_json"]))
+        keys = api._SIMPLE_MODEL_KEYS if fixture == "ref_exec_simple.npz" else api._FULL_MODEL_KEYS
+        assert sorted(keys) == list(_load(fixture)["model_keys"])           # the dict get_model() returns (API.py:21)
         if fixture == "ref_exec_v1.npz":
             ref_wo, mine_wo = dict(ref), norm(mine)
             mine_wo.pop("ortho", None)                      # IANv1.py has no 'ortho' entry (API.py of the product pops it too)
