@@ -72,19 +72,20 @@ def decode(P, z, deconv_fn=deconv):
     return torch.tanh(deconv_fn(h, P["dec_out.W"]))
 
 
-def imgrad(P, c1, r1, c2, r2, z):
-    """API.py:59 -- T.grad(T.mean(X_hat[0,:,r1:r2,c1:c2]), Z) via autograd."""
+def imgrad(P, c1, r1, c2, r2, z, decode_fn=None):
+    """API.py:59 -- T.grad(T.mean(X_hat[0,:,r1:r2,c1:c2]), Z) via autograd.  `decode_fn` selects the graph
+    (default: IAN_simple's decoder; full_decode / v1_decode for the IAN.py / IANv1.py graphs)."""
     z = z.clone().requires_grad_(True)
-    loss = decode(P, z)[0, :, int(r1):int(r2), int(c1):int(c2)].mean()
+    loss = (decode_fn or decode)(P, z)[0, :, int(r1):int(r2), int(c1):int(c2)].mean()
     (g,) = torch.autograd.grad(loss, z)
     return g
 
 
-def imgradRGB(P, c1, r1, c2, r2, RGB, z):
+def imgradRGB(P, c1, r1, c2, r2, RGB, z, decode_fn=None):
     """API.py:64 -- T.grad(T.mean(sqr(-X_hat[0,:,box] + RGB[0,:,box])), Z) via autograd."""
     z = z.clone().requires_grad_(True)
     r1, r2, c1, c2 = int(r1), int(r2), int(c1), int(c2)
-    loss = ((-decode(P, z)[0, :, r1:r2, c1:c2] + RGB[0, :, r1:r2, c1:c2]) ** 2).mean()
+    loss = ((-(decode_fn or decode)(P, z)[0, :, r1:r2, c1:c2] + RGB[0, :, r1:r2, c1:c2]) ** 2).mean()
     (g,) = torch.autograd.grad(loss, z)
     return g
 

@@ -11,7 +11,7 @@ synthetic one of `oracle/weights.py`, written in the `GANcheckpoints` .npz forma
 central differences of the reference forward in float64.
 
     python tests/golden/make_golden_ref.py simple        # ~10 min (three numeric gradients)
-    python tests/golden/make_golden_ref.py v1 full       # ~1 min
+    python tests/golden/make_golden_ref.py v1 full       # ~6 min with the numeric gradients (REF_EXEC_GRADS=0: ~10 s)
 
 The GPU box has no /root/reference: tests read only the committed .npz files.
 """
@@ -156,6 +156,24 @@ def flow_model(which):
     out['xhat_rand'] = fns['X_hat'](gold['z_rand'])
     out['sample_rand'] = fns['sample'](gold['z_rand'])
     print(which, 'done in %.1f s' % (time.time() - t0), flush=True)
+    if os.environ.get('REF_EXEC_GRADS', '1') != '0':
+        # the brush gradients API.py:59,64 would define on this graph (numeric, as for IAN_simple): the target of the
+        # next scope row -- the CUDA path has brush gradients for IAN_simple only
+        r1, r2 = T.scalar('r1', dtype='int32'), T.scalar('r2', dtype='int32')
+        c1, c2 = T.scalar('c', dtype='int32'), T.scalar('c2', dtype='int32')
+        RGB = T.tensor4('RGB', dtype='float32')
+        X_hat = go(model['l_out'], {model['l_Z']: Z}, deterministic=True)
+        lighten = theano.function([c1, r1, c2, r2, Z], T.grad(T.mean(X_hat[0, :, r1:r2, c1:c2]), Z))
+        rgbgrad = theano.function([c1, r1, c2, r2, RGB, Z],
+                                  T.grad(T.mean((T.sqr(-X_hat[0, :, r1:r2, c1:c2] + RGB[0, :, r1:r2, c1:c2]))), Z))
+        box = [20, 24, 33, 37]                                  # c1, r1, c2, r2
+        frame = np.broadcast_to(np.float32([0.3, -0.2, 0.6]).reshape(1, 3, 1, 1), (1, 3, 64, 64)).astype(np.float32)
+        t0 = time.time()
+        out['grad_box'] = np.array(box, np.int32)
+        out['grad_rgb_target'] = np.float32([0.3, -0.2, 0.6])
+        out['g_light'] = lighten(box[0], box[1], box[2], box[3], gold['z_rand'][:1])
+        out['g_rgb'] = rgbgrad(box[0], box[1], box[2], box[3], frame, gold['z_rand'][:1])
+        print(which, 'numeric gradients done in %.1f s' % (time.time() - t0), flush=True)
     path = os.path.join(OUT, 'ref_exec_%s.npz' % which)
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path), 'bytes')

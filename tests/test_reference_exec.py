@@ -106,11 +106,11 @@ def test_fixture_regenerates_from_the_reference(tmp_path):
     """re-execute the reference (IANv1.py: encoder, MADE/IAF, decoder, RGB-Beta head) and compare with the committed file"""
     script = os.path.join(GOLD, "make_golden_ref.py")
     out = subprocess.run([sys.executable, script, "v1"], capture_output=True, text=True, timeout=600,
-                         env=dict(os.environ, REF_EXEC_OUT=str(tmp_path)))
+                         env=dict(os.environ, REF_EXEC_OUT=str(tmp_path), REF_EXEC_GRADS="0"))
     assert out.returncode == 0, out.stderr[-2000:]
     committed, fresh = _load("ref_exec_v1.npz"), np.load(tmp_path / "ref_exec_v1.npz")
-    assert sorted(committed.files) == sorted(fresh.files)
-    for k in committed.files:
+    assert set(fresh.files) <= set(committed.files)          # the quick regeneration skips the numeric gradients
+    for k in fresh.files:
         assert np.array_equal(committed[k], fresh[k]), k
 
 
@@ -130,3 +130,23 @@ def test_product_cfg_dicts_equal_the_reference_config_modules(npe):
             assert ref_wo == mine_wo
         else:
             assert ref == norm(mine), fixture
+
+
+@pytest.mark.parametrize("which", ["v1", "full"])
+def test_flow_model_brush_gradients_match_numeric_gradients_of_executed_reference(which):
+    """oracle-only (the CUDA path has brush gradients for IAN_simple): what API.py:59,64 would
+    compute on the IANv1.py / IAN.py graphs -- autograd through the torch restatement vs central differences of the
+    executed reference forward.  Ready-made target for the next scope row."""
+    import torch
+    from oracle import ian_torch as ot
+    ref = _load("ref_exec_%s.npz" % which)
+    gold = _load("ian_%s_golden.npz" % which)
+    P = ot.to_torch((ow.make_v1_weights if which == "v1" else ow.make_full_weights)(int(gold["weight_seed"])), torch.float64)
+    dec = ot.v1_decode if which == "v1" else ot.full_decode
+    c1, r1, c2, r2 = [int(v) for v in ref["grad_box"]]
+    z = torch.from_numpy(gold["z_rand"][:1].astype(np.float64))
+    frame = torch.from_numpy(np.broadcast_to(ref["grad_rgb_target"].astype(np.float64).reshape(1, 3, 1, 1), (1, 3, 64, 64)).copy())
+    g = ot.imgrad(P, c1, r1, c2, r2, z, decode_fn=dec).numpy()
+    assert np.abs(g - ref["g_light"]).max() <= 1e-5 * np.abs(ref["g_light"]).max()
+    g = ot.imgradRGB(P, c1, r1, c2, r2, frame, z, decode_fn=dec).numpy()
+    assert np.abs(g - ref["g_rgb"]).max() <= 1e-5 * np.abs(ref["g_rgb"]).max()
