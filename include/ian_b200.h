@@ -66,13 +66,31 @@ int ian_create(int model_kind, int device, ian_handle** out);
  * names and shapes: reference GANcheckpoints.py:33-57 + IAN_simple.py layer names).  `data` is a HOST
  * float32 array of `ndim` dims `shape`, in the reference's own layout (conv W (Cout,Cin,5,5); deconv W
  * (Cin,Cout,5,5); dense W (in,out)).  Unlike the reference loader (which only warns,
- * GANcheckpoints.py:45-52) an unknown name or a shape mismatch is an error. */
+ * GANcheckpoints.py:45-52) a name outside ian_model_param_spec's list or a shape mismatch is an error, and so is a
+ * parameter still missing at ian_finalize. */
 int ian_set_param(ian_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
+
+/* The model's OWN parameter list -- what `lasagne.layers.get_all_params(...)` hands GANcheckpoints.load_weights in the
+ * reference (API.py:23-30; GANcheckpoints.py:33-57).  A loader iterates index 0..count-1, looks each `name` up in the
+ * checkpoint and calls ian_set_param; keys of the file that are not in this list (the trainer's `log_sigma_theta`,
+ * discriminator weights, `metadata`) are ignored exactly as the reference loader ignores them.  Handle-free (no GPU
+ * needed).  ian_model_param_count returns the count (or a negative ian_status); `name` stays valid for the life of
+ * the process; `shape` receives 4 entries (trailing ones are 1). */
+int ian_model_param_count(int model_kind);
+int ian_model_param_spec(int model_kind, int index, const char** name, int64_t* shape /*[4]*/, int* ndim);
 
 /* IAN_MODEL_FULL / IAN_MODEL_V1: the MADE input ordering (a permutation of 0..99) from which the autoregressive masks are
  * derived by integer comparison (reference mask_generator.py:29-38,93-94).  Replaces the one
  * `shuffle_ordering` draw of `l_IAF_mu/ls.reset("Once")` (reference API.py:33-36).  Must precede ian_finalize. */
 int ian_set_made_ordering(ian_handle* h, const int32_t* ordering, int n);
+
+/* The 0/1 autoregressive mask the library derives from `ordering` for one MaskedLayer, as (in,out) bytes [100][100]:
+ * which = 0 `<net>_input` (mask_generator.py:93 for layer 0), 1 `<net>_output_W`, 2 `<net>_output_D` (direct
+ * input->output, layers.py:822-836).  Pure host integer logic (handle-free): lets a test compare the mask indexing
+ * bit for bit with the reference's MaskGenerator. */
+int ian_made_mask(const int32_t* ordering, int n, int which, uint8_t* mask_out);
+/* Debug getter: the masked MADE weights W*M as uploaded, float32 [2 nets: mu, ls][3: input, output_W, output_D][100][100]. */
+int ian_debug_made_weights(ian_handle* h, float* out);
 
 /* Check that every parameter of the graph is present, fold BatchNorm (inference), re-lay weights for
  * the kernels and upload them.  Must precede any compute call. */
@@ -128,8 +146,12 @@ int ian_host_free(ian_handle* h, void* p);
  *   ian_reconstruct_gather_dev(h, x, n_local, z, &gathered, stream)   per step
  * The dec_out kernel stores each decoded image straight into slot `rank` of EVERY rank's gather buffer (st.global on
  * peer pointers), then a flag barrier over peer memory makes the step complete: `gathered` (world*n_local,3,64,64)
- * holds all ranks' images on return of the stream work.  Buffers alternate between steps; a result stays valid until
- * the call after next. */
+ * holds all ranks' images on return of the stream work.  n_local may exceed the 512-image plan chunk (the shard then
+ * runs as consecutive chunks into the same gather buffer, one barrier at the end).
+ * Lifetime of a result: the two gather buffers alternate, so step t+1 of ANY rank never touches the buffer that holds
+ * step t -- but a peer that has passed the barrier of step t+1 may begin its step t+2 stores into it.  A result is
+ * therefore valid until the stream work of THIS rank's next call has executed: enqueue every consumer of step t on
+ * `stream` (or order it before) the call of step t+1.  tests/test_gpu_multi.py skews the ranks to check exactly this. */
 int ian_gather_create(ian_handle* h, int world, int rank, int n_local, void* ipc_handle_out /*64 bytes*/);
 int ian_gather_connect(ian_handle* h, const void* all_handles /*world x 64 bytes*/);
 int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out /*nullable*/, float** gathered_out,

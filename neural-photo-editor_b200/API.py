@@ -73,6 +73,38 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+def _z(a, what='z'):
+    """latents: float32 (n,100).  The C side assumes the trailing dimension; theano would raise a shape error."""
+    a = _f32(a, 2, what)
+    if a.shape[1] != 100:
+        raise ValueError("%s must be (n,100), got %r" % (what, a.shape))
+    return a
+
+
+def _img(a, what='images'):
+    """images: float32 (n,3,64,64) NCHW."""
+    a = _f32(a, 4, what)
+    if a.shape[1:] != (3, 64, 64):
+        raise ValueError("%s must be (n,3,64,64), got %r" % (what, a.shape))
+    return a
+
+
+def model_param_specs(kind):
+    """[(name, shape)] of the graph's own parameters, in the reference's checkpoint naming -- the list API.py:23-28
+    builds with lasagne.layers.get_all_params and hands to GANcheckpoints.load_weights."""
+    lib = _lib.load()
+    n = lib.ian_model_param_count(int(kind))
+    if n < 0:
+        raise ValueError("unknown model kind %r" % (kind,))
+    out = []
+    for i in range(n):
+        name, shape, nd = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+        if lib.ian_model_param_spec(int(kind), i, C.byref(name), shape, C.byref(nd)) != _lib.IAN_OK:
+            raise RuntimeError("ian_model_param_spec(%d, %d) failed" % (kind, i))
+        out.append((name.value.decode(), tuple(int(shape[k]) for k in range(nd.value))))
+    return out
+
+
 class IAN:
     """Generic class for using IAN style models with the NPE (reference API.py:11)."""
 
@@ -107,14 +139,20 @@ class IAN:
         print('Loading weights')
         if weights is None:
             weights = np.load(self.weights_fname, allow_pickle=False)
-        for name in weights.keys() if hasattr(weights, 'keys') else weights:
-            if name == 'metadata':
-                continue
+        # GANcheckpoints.load_weights (reference GANcheckpoints.py:33-57): iterate the MODEL's parameters and look each
+        # one up by name; keys of the file the graph does not own (the trainer's log_sigma_theta,
+        # train_IAN_simple.py:300,564; discriminator weights; the pickled 'metadata') are ignored.  Where the reference
+        # only warns -- a parameter missing from the file, a shape mismatch -- this loader raises (ian_set_param /
+        # ian_finalize), because a silently half-loaded model is never what a caller wants.
+        have = set(weights.keys() if hasattr(weights, 'keys') else weights)
+        own = model_param_specs(kind)
+        for name, _shape in own:
+            if name not in have:
+                continue                                    # reported by ian_finalize as "missing parameter"
             arr = np.ascontiguousarray(np.asarray(weights[name], dtype=np.float32))
-            if name.startswith('minibatch_discrim.') or name.startswith('discrimi.'):
-                continue   # discriminator head: not on the hot path (IAN_simple.py:225-231)
-            shape = (C.c_int64 * arr.ndim)(*arr.shape)
+            shape = (C.c_int64 * max(arr.ndim, 1))(*arr.shape)
             self._check(self._lib.ian_set_param(self._h, name.encode(), _fp(arr), shape, arr.ndim))
+        self.ignored_keys = sorted(have - {n for n, _ in own})
         if kind != _lib.IAN_MODEL_SIMPLE:
             print('Shuffling MADE masks')                   # reference API.py:33-36
             o = np.ascontiguousarray(globals()['made_ordering']() if made_ordering is None else made_ordering, np.int32)
@@ -168,7 +206,7 @@ class IAN:
 
     def _imgrad(self, c1, r1, c2, r2, RGB, z):
         c1, r1, c2, r2 = (_int_scalar(v, n) for v, n in zip((c1, r1, c2, r2), ('c1', 'r1', 'c2', 'r2')))
-        z = _f32(z, 2, 'z')
+        z = _z(z)
         out = np.zeros_like(z)        # only sample 0 is differentiated (API.py:59,64)
         if z.shape[0] == 0:
             return out
@@ -202,9 +240,7 @@ class IAN:
 
     def sample_at(self, z):
         """Decode images z => x: (n, zdim) float32 -> (n,3,s,s) in [-1,1] (reference API.py:98-110)."""
-        z = _f32(z, 2, 'z')
-        if z.shape[1] != 100:
-            raise ValueError("z must be (n,100), got %r" % (z.shape,))
+        z = _z(z)
         x = np.empty((z.shape[0], 3, 64, 64), np.float32)
         if z.shape[0]:
             self._check(self._lib.ian_decode_host(self._h, _fp(z), z.shape[0], _fp(x)))
@@ -213,20 +249,20 @@ class IAN:
     # ---- extensions (batched / reparameterised / fused) ------------------------------------------
     def encode(self, images, eps=None):
         """deterministic (eps=None): mu(x).  With eps (n,100): mu + exp(logsigma)*eps (layers.py:419-433)."""
-        x = _f32(images, 4, 'images')
-        if x.shape[1:] != (3, 64, 64):
-            raise ValueError("images must be (n,3,64,64), got %r" % (x.shape,))
+        x = _img(images)
         n = x.shape[0]
         z = np.empty((n, 100), np.float32)
         if n:
-            e = None if eps is None else _f32(eps, 2, 'eps')
+            e = None if eps is None else _z(eps, 'eps')
+            if e is not None and e.shape[0] != n:
+                raise ValueError("eps must be (%d,100), got %r" % (n, e.shape))
             self._check(self._lib.ian_encode_host(self._h, _fp(x), n, _fp(e) if e is not None else None, _fp(z)))
         return z
 
     # ---- the reference sampling script's function set (sample_IAN.py:86-94) ---------------------------------
     def Zfn(self, images):
         """X -> l_Z_IAF, deterministic (= mu, before the MADE/IAF flow); sample_IAN.py:91."""
-        x = _f32(images, 4, 'images')
+        x = _img(images)
         z = np.empty((x.shape[0], 100), np.float32)
         if x.shape[0]:
             self._check(self._lib.ian_encode_pre_host(self._h, _fp(x), x.shape[0], _fp(z)))
@@ -234,7 +270,7 @@ class IAN:
 
     def Z_IAF_fn(self, z_iaf):
         """l_Z_IAF -> l_Z through the MADE/IAF flow (identity for IAN_simple); sample_IAN.py:94."""
-        z0 = _f32(z_iaf, 2, 'z')
+        z0 = _z(z_iaf)
         z = np.empty_like(z0)
         if z0.shape[0]:
             self._check(self._lib.ian_flow_host(self._h, _fp(z0), z0.shape[0], _fp(z), None))
@@ -242,7 +278,7 @@ class IAN:
 
     def sample(self, z_iaf):
         """l_Z_IAF -> X: flow, then decoder; sample_IAN.py:86 (what the script feeds N(0,1) noise to)."""
-        z0 = _f32(z_iaf, 2, 'z')
+        z0 = _z(z_iaf)
         x = np.empty((z0.shape[0], 3, 64, 64), np.float32)
         if z0.shape[0]:
             self._check(self._lib.ian_flow_host(self._h, _fp(z0), z0.shape[0], None, _fp(x)))
@@ -257,7 +293,7 @@ class IAN:
         endpoint].  `endpoints`: 6 images float32 (6,3,64,64) in [-1,1].  Returns float32 images in [-1,1]."""
         rng = np.random.RandomState(seed)
         samples = self.sample(rng.randn(n_samples, 100).astype(np.float32))
-        ends = _f32(endpoints, 4, 'endpoints')
+        ends = _img(endpoints, 'endpoints')
         Ze = self.Zfn(ends)
         Z = np.asarray([Ze[2 * i] * (1 - j) + Ze[2 * i + 1] * j for i in range(3) for j in [t / 6.0 for t in range(7)]],
                        dtype=np.float32)
@@ -267,7 +303,7 @@ class IAN:
     def reconstruct(self, images, return_z=False, out=None):
         """encode -> decode in one library call (the BASELINE metric's path).  `out`: optional preallocated
         float32 (n,3,64,64) result buffer (e.g. from pinned_empty) to avoid a pageable allocation per call."""
-        x = _f32(images, 4, 'images')
+        x = _img(images)
         n = x.shape[0]
         xh = np.empty_like(x) if out is None else self._out(out, x.shape)
         z = np.empty((n, 100), np.float32)
@@ -294,7 +330,7 @@ class IAN:
         """Pipelined encode -> decode: enqueue one batch (n <= 512) and return a ticket immediately; `out`
         (and `z_out`) receive the result once reconstruct_wait(ticket) returns.  Two requests may be in
         flight; use pinned_empty() buffers so the copies overlap the neighbouring requests' compute."""
-        x = _f32(images, 4, 'images')
+        x = _img(images)
         n = x.shape[0]
         out = self._out(out, x.shape)
         if z_out is not None:
@@ -314,7 +350,7 @@ class IAN:
         later calls): consume it before advancing the generator twice, and run one stream at a time."""
         outs, pending = self._stream_outs, None              # page-locking costs milliseconds: keep the buffers
         for i, x in enumerate(batches):
-            x = _f32(x, 4, 'images')
+            x = _img(x)
             key = (i & 1, x.shape)
             if key not in outs:
                 outs[key] = self.pinned_empty(x.shape)
@@ -339,7 +375,7 @@ class IAN:
 
     def grad(self, z, boxes, rgb=None):
         """Per-sample brush gradient: boxes (n,4) int32 [c1,r1,c2,r2]; rgb None (lighten), (n,3) or frames."""
-        z = _f32(z, 2, 'z')
+        z = _z(z)
         n = z.shape[0]
         boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(n, 4))
         t, is_frame = self._target(rgb, n)
@@ -350,7 +386,7 @@ class IAN:
 
     def edit_steps(self, z, boxes, rgb=None, n_steps=32, weight=0.05):
         """n_steps of the NPE paint rule per sample: Z <- Z - weight*g*(1+(x2-x1)) (reference NPE.py:199-209)."""
-        z = _f32(z, 2, 'z').copy()
+        z = _z(z).copy()
         n = z.shape[0]
         boxes = np.ascontiguousarray(np.asarray(boxes, dtype=np.int32).reshape(n, 4))
         t, is_frame = self._target(rgb, n)

@@ -20,7 +20,11 @@ _H = C.c_void_p
 SIGNATURES = {
     "ian_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_H)]),
     "ian_set_param": (C.c_int, [_H, C.c_char_p, _F, C.POINTER(C.c_int64), C.c_int]),
+    "ian_model_param_count": (C.c_int, [C.c_int]),
+    "ian_model_param_spec": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "ian_set_made_ordering": (C.c_int, [_H, _I, C.c_int]),
+    "ian_made_mask": (C.c_int, [_I, C.c_int, C.c_int, C.c_void_p]),
+    "ian_debug_made_weights": (C.c_int, [_H, _F]),
     "ian_finalize": (C.c_int, [_H]),
     "ian_destroy": (C.c_int, [_H]),
     "ian_last_error": (C.c_char_p, [_H]),

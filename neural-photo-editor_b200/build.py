@@ -1,34 +1,58 @@
 """Build libian_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python neural-photo-editor_b200/build.py [--force]
+
+Every .cu is compiled to its own object (in parallel, only when stale) and the objects are linked into the shared
+library; objects live under csrc/_obj/ (git-ignored; they travel to the GPU box with the .so so nothing rebuilds there).
 """
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["ian_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "decout_tc.cu", "conv1_tc.cu", "edge_kernels.cu"]
+SRC = ["ian_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "decout_tc.cu", "conv1_tc.cu", "edge_kernels.cu",
+       "head_tc.cu", "train_kernels.cu"]
 HDR = ["tapgemm.h", "edge.h", "tc_ptx.cuh", "../../include/ian_b200.h"]
 LIB = os.path.join(HERE, "libian_b200.so")
+OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, "csrc", f) for f in SRC + HDR] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+def _sources():
+    return [f for f in SRC if os.path.exists(os.path.join(HERE, "csrc", f))]
+
+
+def _stale_objects(force: bool):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_hdr = max([os.path.getmtime(os.path.join(HERE, "csrc", f)) for f in HDR] + [os.path.getmtime(os.path.abspath(__file__))])
+    out = []
+    for f in _sources():
+        src, obj = os.path.join(HERE, "csrc", f), os.path.join(OBJ_DIR, f[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_hdr):
+            out.append((src, obj))
+    return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(HERE, "csrc", f) for f in SRC]
+    todo = _stale_objects(force)
+    objs = [os.path.join(OBJ_DIR, f[:-3] + ".o") for f in _sources()]
+    if not todo and os.path.exists(LIB) and all(os.path.getmtime(o) <= os.path.getmtime(LIB) for o in objs):
+        return LIB
+
+    def cc(job):
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", job[0], "-o", job[1]]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        list(ex.map(cc, todo))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -262,15 +262,13 @@ void conv1_free_maps(Conv1Maps* m) { delete m; }
 
 int launch_conv1_tc(const Conv1Maps* maps, const float* x, const float* bias, __nv_bfloat16* out, long long plane, int n,
                     cudaStream_t st) {
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  const int dev = cur_device();
+  if (!attr_set.is_done(dev)) {
     if (cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
+    attr_set.set_done(dev);
   }
+  const int num_sms = tc_num_sms();
   const int total = n * kTilesPerImage;
   const int grid = total < num_sms ? total : num_sms;
   conv1_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*maps, x, bias, out, plane, n);

@@ -265,15 +265,13 @@ DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n
 void decout_free_maps(DecOutMaps* m) { delete m; }
 
 int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int n, cudaStream_t st) {
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  const int dev = cur_device();
+  if (!attr_set.is_done(dev)) {
     if (cudaFuncSetAttribute(decout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_set = true;
+    attr_set.set_done(dev);
   }
+  const int num_sms = tc_num_sms();
   const int total = n * kItemsPerImage;
   const int grid = total < num_sms ? total : num_sms;
   if (ndst < 1 || ndst > kMaxPeers) return -1;

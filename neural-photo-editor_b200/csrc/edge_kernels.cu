@@ -213,10 +213,13 @@ __global__ void __launch_bounds__(256) brush_seed_bwd_kernel(const float* __rest
   const int c4 = (int)(idx & 31) * 4;
   const long long pix = idx >> 5;
   const int b = (int)(pix & 31), a = (int)((pix >> 5) & 31), k = (int)(pix >> 10);
-  const int c1 = boxes[k * 4 + 0], r1 = boxes[k * 4 + 1], c2 = boxes[k * 4 + 2], r2 = boxes[k * 4 + 3];
+  // device-resident boxes cannot be validated on the host: clamp to the frame here (never read outside x_hat); an
+  // empty box contributes nothing and brush_update_kernel turns its gradient into NaN (mean over an empty slice)
+  const int c1 = max(boxes[k * 4 + 0], 0), r1 = max(boxes[k * 4 + 1], 0);
+  const int c2 = min(boxes[k * 4 + 2], 64), r2 = min(boxes[k * 4 + 3], 64);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   // rows u = 2+2a-ki, ki in 0..4  ->  u in [2a-2, 2a+2]
-  if (2 * a + 2 >= r1 && 2 * a - 2 < r2 && 2 * b + 2 >= c1 && 2 * b - 2 < c2) {
+  if (r1 < r2 && c1 < c2 && 2 * a + 2 >= r1 && 2 * a - 2 < r2 && 2 * b + 2 >= c1 && 2 * b - 2 < c2) {
     const float inv = 1.f / (3.f * (float)(r2 - r1) * (float)(c2 - c1));
     for (int ki = 0; ki < 5; ++ki) {
       const int u = 2 + 2 * a - ki;
@@ -263,7 +266,9 @@ __global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_
   const int k = i / 128, j = i % 128;
   float zv = 0.f;
   if (j < 100) {
-    const float gv = gpad[i];
+    const int bc1 = max(boxes[k * 4 + 0], 0), br1 = max(boxes[k * 4 + 1], 0);
+    const int bc2 = min(boxes[k * 4 + 2], 64), br2 = min(boxes[k * 4 + 3], 64);
+    const float gv = (bc1 < bc2 && br1 < br2) ? gpad[i] : __int_as_float(0x7fc00000);   // empty box: NaN, as the reference
     if (g_out) g_out[k * 100 + j] = gv;
     if (z) {
       const float fac = 1.f + (float)(boxes[k * 4 + 2] - boxes[k * 4 + 0]);
@@ -501,10 +506,11 @@ int launch_conv1(const float* x, const float* wt, const float* bias, __nv_bfloat
 int dec_out_smem_bytes() { return (DO_P * DO_P * DO_LD + 25 * 128 * 4) * (int)sizeof(float); }
 
 int launch_dec_out(const __nv_bfloat16* h3, long long plane, const float* wt, float* xhat, int n, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(dec_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_out_smem_bytes());
-    attr_set = true;
+  static DeviceOnce attr_set;
+  const int dev = cur_device();
+  if (!attr_set.is_done(dev)) {
+    if (cudaFuncSetAttribute(dec_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_out_smem_bytes()) != cudaSuccess) return -1;
+    attr_set.set_done(dev);
   }
   dec_out_kernel<<<n * 16, 256, dec_out_smem_bytes(), st>>>(h3, plane, wt, xhat, n);
   return CHECK_LAUNCH();

@@ -174,6 +174,8 @@ struct ian_handle {
   bool gconnected = false;
   float** gather_dsts = nullptr;               // non-null only inside ian_reconstruct_gather_dev
   long long tickets = 0;
+  struct Ticket { int id = -1, n = 0, slot = 0; };
+  Ticket inflight[2];          // the two most recent pipelined requests (ian_reconstruct_submit)
   std::string err;
   int64_t launches = 0;
   std::map<std::string, HostParam> params;
@@ -959,6 +961,14 @@ void mdc_composite(ian_handle* h, const std::string& name, int F, int C, const s
   }
 }
 
+// MADE connectivity (reference mask_generator.py:29-38,93-94 as API.IAN leaves it after reset("Once")): with ordering o,
+// layer connectivities are input = o + 1, hidden = 1, output = o and a weight (i -> j) survives iff
+// conn_in[i] <= conn_out[j].  which: 0 = `_input` (input -> hidden), 1 = `_output_W` (hidden -> output),
+// 2 = `_output_D` (input -> output, direct).  Integer comparisons only: W * M is bit-exact.
+inline bool made_keep(const int32_t* o, int which, int i, int j) {
+  return which == 0 ? (o[i] + 1 <= 1) : which == 1 ? (1 <= o[j]) : (o[i] + 1 <= o[j]);
+}
+
 int prepare_made(ian_handle* h) {
   // ---- MADE (layers.py:653-853): masks from the ordering (mask_generator.py:93-94), integer
   // comparisons, multiplied into the float32 weights here on the host (bit-exact W*M)
@@ -974,8 +984,7 @@ int prepare_made(ian_handle* h) {
         const auto& b = P(h, (std::string(nets[net]) + subs[m] + ".b").c_str()).data;
         for (int i = 0; i < 100; ++i)
           for (int j = 0; j < 100; ++j) {
-            // connectivity: input = o+1, hidden = 1, output = o
-            const bool keep = m == 0 ? (o[i] + 1 <= 1) : m == 1 ? (1 <= o[j]) : (o[i] + 1 <= o[j]);
+            const bool keep = made_keep(o.data(), m, i, j);
             mw[((net * 3 + m) * 100 + i) * 100 + j] = keep ? W[i * 100 + j] : 0.f;
           }
         for (int j = 0; j < 100; ++j) mb[(net * 3 + m) * 100 + j] = b[j];
@@ -1197,7 +1206,7 @@ int ian_create(int model_kind, int device, ian_handle** out) {
     delete h;
     return fail(nullptr, IAN_ERR_CUDA, "cudaStreamCreate failed");
   }
-  if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v; }
+  if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v > 4096 ? 4096 : v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
   if (const char* c = getenv("IAN_STREAMK")) h->streamk = atoi(c) != 0;
   if (const char* c = getenv("IAN_GRAPHS")) h->graphs = atoi(c) != 0;
@@ -1237,6 +1246,46 @@ int ian_set_made_ordering(ian_handle* h, const int32_t* ordering, int n) {
     seen[ordering[i]] = 1;
   }
   h->made_ordering.assign(ordering, ordering + n);
+  return IAN_OK;
+}
+
+// The model's OWN parameter list: what `lasagne.layers.get_all_params(...)` hands GANcheckpoints.load_weights in the
+// reference (API.py:23-30).  A loader iterates these names and looks each one up in the checkpoint, so that extra keys
+// of the file (log_sigma_theta, discriminator weights, metadata ...) are ignored exactly as the reference does.
+static const std::vector<Spec>& cached_specs(int kind) {
+  static std::vector<Spec> cache[3];
+  static bool built[3] = {false, false, false};
+  if (!built[kind]) { cache[kind] = spec_list(kind); built[kind] = true; }
+  return cache[kind];
+}
+
+int ian_model_param_count(int model_kind) {
+  if (model_kind < 0 || model_kind > 2) return IAN_ERR_INVALID;
+  return (int)cached_specs(model_kind).size();
+}
+
+int ian_model_param_spec(int model_kind, int index, const char** name, int64_t* shape /*[4]*/, int* ndim) {
+  if (model_kind < 0 || model_kind > 2 || !name || !shape || !ndim) return IAN_ERR_INVALID;
+  const auto& v = cached_specs(model_kind);
+  if (index < 0 || index >= (int)v.size()) return IAN_ERR_INVALID;
+  *name = v[index].name.c_str();
+  *ndim = (int)v[index].shape.size();
+  for (int i = 0; i < 4; ++i) shape[i] = i < *ndim ? v[index].shape[i] : 1;
+  return IAN_OK;
+}
+
+int ian_made_mask(const int32_t* ordering, int n, int which, uint8_t* mask_out /*[100][100], (in,out)*/) {
+  if (!ordering || !mask_out || n != 100 || which < 0 || which > 2) return IAN_ERR_INVALID;
+  for (int i = 0; i < 100; ++i)
+    for (int j = 0; j < 100; ++j) mask_out[i * 100 + j] = made_keep(ordering, which, i, j) ? 1 : 0;
+  return IAN_OK;
+}
+
+int ian_debug_made_weights(ian_handle* h, float* out /*[2][3][100][100]*/) {
+  if (!h || !out) return IAN_ERR_INVALID;
+  if (!h->finalized || !h->made_w) return fail(h, IAN_ERR_STATE, "no MADE weights on this handle (IAN_simple, or not finalized)");
+  DeviceGuard dg(h->device);
+  CUDA_TRY(h, cudaMemcpy(out, h->made_w, (size_t)2 * 3 * 10000 * sizeof(float), cudaMemcpyDeviceToHost));
   return IAN_OK;
 }
 
@@ -1560,6 +1609,10 @@ int ian_reconstruct_submit(ian_handle* h, const float* x, int n, float* z_out, f
   Plan* pl = nullptr;
   if ((rc = get_plan(h, n, &pl)) != IAN_OK) return rc;
   const int s = (int)(h->tickets & 1);
+  if (h->inflight[s].id >= 0) {                          // the request that used this slot two submits ago (any plan) is done
+    auto prev = h->plans.find(h->inflight[s].n);
+    if (prev != h->plans.end() && prev->second->ev_d2h[s]) CUDA_TRY(h, cudaEventSynchronize(prev->second->ev_d2h[s]));
+  }
   if (!pl->sx[s]) {
     for (int b = 0; b < 2; ++b) {
       if ((rc = alloc_buf(h, pl, pl->sx[b], (long long)n * 12288)) != IAN_OK) return rc;
@@ -1570,8 +1623,6 @@ int ian_reconstruct_submit(ian_handle* h, const float* x, int n, float* z_out, f
       CUDA_TRY(h, cudaEventCreateWithFlags(&pl->ev_d2h[b], cudaEventDisableTiming));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));     // the memsets of the new buffers
-  } else {
-    CUDA_TRY(h, cudaEventSynchronize(pl->ev_d2h[s]));  // the request that used this slot two submits ago is done
   }
   CUDA_TRY(h, cudaMemcpyAsync(pl->sx[s], x, (size_t)n * 12288 * 4, cudaMemcpyHostToDevice, h->h2d_stream));
   CUDA_TRY(h, cudaEventRecord(pl->ev_h2d[s], h->h2d_stream));
@@ -1583,18 +1634,23 @@ int ian_reconstruct_submit(ian_handle* h, const float* x, int n, float* z_out, f
   CUDA_TRY(h, cudaMemcpyAsync(x_hat, pl->sxh[s], (size_t)n * 12288 * 4, cudaMemcpyDeviceToHost, h->d2h_stream));
   if (z_out) CUDA_TRY(h, cudaMemcpyAsync(z_out, pl->sz[s], (size_t)n * 400, cudaMemcpyDeviceToHost, h->d2h_stream));
   CUDA_TRY(h, cudaEventRecord(pl->ev_d2h[s], h->d2h_stream));
-  *ticket = (int)(((h->tickets & 1) << 16) | (unsigned)n);   // slot parity in bit 16, batch size in the low bits
+  const int id = (int)(h->tickets & 0x7fffffff);             // monotonically increasing; mapped to (plan, slot) below
+  h->inflight[s].id = id; h->inflight[s].n = n; h->inflight[s].slot = s;
+  *ticket = id;
   h->tickets += 1;
   return IAN_OK;
 }
 
 int ian_reconstruct_wait(ian_handle* h, int ticket) {
   if (!h) return IAN_ERR_INVALID;
-  const int n = ticket & 0xffff, s = (ticket >> 16) & 1;
-  auto it = h->plans.find(n);
-  if (it == h->plans.end() || !it->second->ev_d2h[s]) return fail(h, IAN_ERR_INVALID, "unknown ticket %d", ticket);
+  if (ticket < 0 || (long long)ticket >= h->tickets) return fail(h, IAN_ERR_INVALID, "unknown ticket %d", ticket);
+  const ian_handle::Ticket* tk = nullptr;
+  for (const auto& t : h->inflight) if (t.id == ticket) tk = &t;
+  if (!tk) return IAN_OK;      // older than the two requests in flight: its slot was reused, i.e. it completed (submit waited)
+  auto it = h->plans.find(tk->n);
+  if (it == h->plans.end() || !it->second->ev_d2h[tk->slot]) return fail(h, IAN_ERR_INVALID, "unknown ticket %d", ticket);
   DeviceGuard dg(h->device);
-  CUDA_TRY(h, cudaEventSynchronize(it->second->ev_d2h[s]));
+  CUDA_TRY(h, cudaEventSynchronize(it->second->ev_d2h[tk->slot]));
   return IAN_OK;
 }
 

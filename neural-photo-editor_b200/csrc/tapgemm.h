@@ -20,9 +20,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace ian {
 
 enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_ELU = 3, ACT_MASK = 4 };
+
+// Function attributes (max dynamic shared memory) and the SM count are PER DEVICE, and one process may hold handles on
+// several GPUs (API.IAN(..., device=k)): every launcher keeps its one-time setup in an array indexed by the current
+// device.  Setting an attribute twice is harmless, so the flags only need to be tear-free.
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+struct DeviceOnce {
+  std::atomic<bool> done[kMaxDevices];
+  bool is_done(int dev) const { return done[dev].load(std::memory_order_acquire); }
+  void set_done(int dev) { done[dev].store(true, std::memory_order_release); }
+};
 
 constexpr int kMaxTaps = 40;
 constexpr int kMaxPhases = 4;

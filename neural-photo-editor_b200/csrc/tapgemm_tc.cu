@@ -550,13 +550,14 @@ void tc_free_maps(TcMaps* m) { delete m; }
 int tc_tile_width(const TcMaps* maps) { return maps->BN; }
 
 int tc_num_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static std::atomic<int> num_sms[kMaxDevices];
+  const int dev = cur_device();
+  int n = num_sms[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    num_sms[dev].store(n, std::memory_order_relaxed);
   }
-  return num_sms;
+  return n;
 }
 size_t tc_sk_workspace_floats() { return (size_t)tc_num_sms() * kEpiWarps * 32 * 128; }
 size_t tc_sk_flag_ints() { return (size_t)tc_num_sms() * kEpiWarps; }
@@ -564,11 +565,12 @@ size_t tc_sk_flag_ints() { return (size_t)tc_num_sms() * kEpiWarps; }
 template <int BN, int PASSES, int MT, bool SK>
 static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<BN, PASSES, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  const int dev = cur_device();
+  if (!attr_set.is_done(dev)) {
     if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
-    attr_set = true;
+    attr_set.set_done(dev);
   }
   int total_work, grid;
   if (SK) {                                              // T K-steps, one CTA per SM, every CTA gets T/G of them

@@ -293,10 +293,18 @@ def test_loader_rejects_bad_checkpoints(npe, weights):
     missing = {k: v for k, v in weights.items() if k != "bnorm3.inv_std"}
     with pytest.raises(npe.IanError):
         npe.IAN("IAN_simple.py", True, weights=missing)
-    extra = dict(weights)
-    extra["not_a_layer.W"] = np.zeros((1,), np.float32)
-    with pytest.raises(npe.IanError):
-        npe.IAN("IAN_simple.py", True, weights=extra)
+    extra = dict(weights)                                          # keys the graph does not own are ignored, as in
+    extra["not_a_layer.W"] = np.zeros((1,), np.float32)            # GANcheckpoints.load_weights (it iterates the MODEL's params)
+    ok = npe.IAN("IAN_simple.py", True, weights=extra)
+    assert ok.ignored_keys == ["not_a_layer.W"]
+    ok.close()
+    lib = npe.load()                                               # ... but the C-ABI itself refuses a name outside its list
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.ian_create(0, 0, C.byref(h)) == 0
+    one = np.zeros((1,), np.float32)
+    assert lib.ian_set_param(h, b"not_a_layer.W", one.ctypes.data_as(C.POINTER(C.c_float)), (C.c_int64 * 1)(1), 1) < 0
+    lib.ian_destroy(h)
 
 
 def test_native_library_is_the_compute_path(model):
