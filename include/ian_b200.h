@@ -156,6 +156,16 @@ int ian_gather_create(ian_handle* h, int world, int rank, int n_local, void* ipc
 int ian_gather_connect(ian_handle* h, const void* all_handles /*world x 64 bytes*/);
 int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out /*nullable*/, float** gathered_out,
                                void* stream);
+/* Pipelined form of the same all-gather, for streams of batches.  dec_out's peer stores are bound by the NVLink
+ * egress (7 x 12.6 MB per GPU and step at 8 x 256 images: ~0.11 ms of link time behind a 0.04 ms kernel), so here the
+ * shard is decoded into this rank's own buffer and a small copy kernel on a side stream pushes it to every peer
+ * WHILE the next step's tensor kernels run; a free/pushed flag handshake over peer memory orders the buffer reuse
+ * across ranks.  ian_reconstruct_gather_async_dev enqueues one step and returns; ian_gather_wait_dev makes `stream`
+ * wait until the most recent step's images of ALL ranks have landed and returns that buffer.  A result must be
+ * consumed (in stream order) before the call that submits the step after next.  Steps are collective: every rank
+ * calls the same sequence of gather entry points. */
+int ian_reconstruct_gather_async_dev(ian_handle* h, const float* x, int n_local, float* z_out /*nullable*/, void* stream);
+int ian_gather_wait_dev(ian_handle* h, float** gathered_out, void* stream);
 
 /* ---- the function set of the reference's sampling script (reference sample_IAN.py:86-94) ---------------------
  *   Zfn      : X -> l_Z_IAF (deterministic = mu, before the MADE/IAF flow)        -> ian_encode_pre_host

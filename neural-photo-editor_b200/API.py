@@ -443,6 +443,42 @@ class IAN:
                                                          stream or None))
         return out.value
 
+    def reconstruct_gather_async_dev(self, x_ptr, n_local, z_ptr=0, stream=0):
+        """pipelined form: enqueue this rank's shard; a side-stream copy kernel pushes it to the peers while the next
+        call computes.  gather_wait_dev() returns the complete buffer of the most recent step."""
+        self._check(self._lib.ian_reconstruct_gather_async_dev(self._h, x_ptr, int(n_local), z_ptr or None, stream or None))
+
+    def gather_wait_dev(self, stream=0):
+        out = C.c_void_p()
+        self._check(self._lib.ian_gather_wait_dev(self._h, C.byref(out), stream or None))
+        return out.value
+
+    def reconstruct_sharded(self, x, group=None, stream=0, pipelined=False):
+        """Data-parallel encode -> decode of a FULL batch held by every rank (torch CUDA tensor (N,3,64,64) float32, N
+        divisible by the world size): this rank computes shard `parallel.shard_bounds(N, rank, world)` and the decoded
+        shards are all-gathered by the library (peer stores over NVLink).  Returns a torch tensor VIEW (N,3,64,64) of
+        the library's gather buffer (valid until the next call's stream work; see include/ian_b200.h)."""
+        import torch
+        import torch.distributed as dist
+        from . import parallel
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = int(x.shape[0])
+        lo, hi = parallel.shard_bounds(n, rank, world)
+        if n % world:
+            raise ValueError("reconstruct_sharded needs a batch divisible by the world size (got %d over %d ranks); "
+                             "parallel.sharded_reconstruct handles ragged shards with a separate all_gather" % (n, world))
+        if getattr(self, '_gather_n', None) != hi - lo or getattr(self, '_gather_world', None) != world:
+            if getattr(self, '_gather_n', None) is not None:
+                raise _lib.IanError("gather buffers were sized for %d images per rank" % self._gather_n)
+            self.setup_fused_gather(hi - lo, group)
+        shard = x[lo:hi]
+        if pipelined:
+            self.reconstruct_gather_async_dev(shard.data_ptr(), hi - lo, 0, stream)
+            ptr = self.gather_wait_dev(stream)
+        else:
+            ptr = self.reconstruct_gather_dev(shard.data_ptr(), hi - lo, 0, stream)
+        return parallel.as_cuda_tensor(ptr, (n, 3, 64, 64), x.device)
+
     # ---- device-pointer variants (ints from torch.Tensor.data_ptr(); no host copies, async) ----------
     def reconstruct_dev(self, x_ptr, n, z_ptr, xhat_ptr, stream=0):
         self._check(self._lib.ian_reconstruct_dev(self._h, x_ptr, n, z_ptr or None, xhat_ptr, stream or None))

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ian_gather_create": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ian_gather_connect": (C.c_int, [_H, C.c_void_p]),
     "ian_reconstruct_gather_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ian_reconstruct_gather_async_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ian_gather_wait_dev": (C.c_int, [_H, C.POINTER(C.c_void_p), C.c_void_p]),
     "ian_encode_pre_host": (C.c_int, [_H, _F, C.c_int, _F]),
     "ian_flow_host": (C.c_int, [_H, _F, C.c_int, _F, _F]),
     "ian_grad_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -221,7 +221,87 @@ __global__ void peer_wait_kernel(const int* my_flags, int world, int epoch) {
   } while (v < epoch);
 }
 
+// ---- pipelined all-gather: the decoded shard of step t is pushed to the peers by this small copy kernel on a side
+// stream WHILE the tensor kernels of step t+1 run on the main stream (8 GPUs: 7 x 12.6 MB leave each GPU per step; at
+// the measured ~770 GB/s per direction that is 0.11 ms of link time, which the 40 us dec_out kernel cannot hide but a
+// 1.6 ms step can).  Flags (int, in every rank's own allocation, written by the peers with release.sys stores):
+//   free[r]   = t : rank r is done with the gather buffer half that step t writes (its consumer of step t-2 has run)
+//   pushed[r] = t : rank r's shard of step t has landed in this rank's buffer
+// Block 0 publishes this rank's free[t]; every block waits for peer p's free[t] before its first store to p; the last
+// block to finish publishes pushed[t] to everybody.
+struct PushArgs {
+  const float* src;                 // this rank's shard inside its own gather buffer
+  float* dst[kMaxPeers];            // the same slot inside every rank's buffer (dst[rank] unused)
+  int* flags[kMaxPeers];            // every rank's flag block: [0,8) barrier, [8,16) free, [16,24) pushed, [24] counter
+  long long n_vec;                  // uint4 elements of the shard
+  int world, rank, step;
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) peer_push_kernel(const PushArgs a) {
+  int* my_flags = a.flags[a.rank];
+  if (blockIdx.x == 0 && threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
+    __threadfence_system();
+    st_release_sys(a.flags[threadIdx.x] + 8 + a.rank, a.step);          // my half for step t is free
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(a.src);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int k = 1; k < a.world; ++k) {
+    const int p = (a.rank + k) % a.world;                                // ring order: spreads the switch ports
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      while (ld_acquire_sys(my_flags + 8 + p) < a.step)
+        if (clock64() - t0 > 20000000000LL) __trap();                    // ~10 s: a peer died
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(a.dst[p]);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < a.n_vec; i += 4 * stride) {                  // 4 independent 16-byte loads in flight per thread
+      const uint4 v0 = __ldg(src + i), v1 = __ldg(src + i + stride), v2 = __ldg(src + i + 2 * stride), v3 = __ldg(src + i + 3 * stride);
+      dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+    }
+    for (; i < a.n_vec; i += stride) dst[i] = __ldg(src + i);
+  }
+  __threadfence_system();                                                // my peer stores before the flag
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(my_flags + 24, 1);
+    if (done == (int)gridDim.x - 1) {
+      my_flags[24] = 0;                                                  // re-arm for the next launch (stream-ordered)
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + 16 + a.rank, a.step);
+    }
+  }
+}
+
+__global__ void peer_wait_pushed_kernel(const int* my_flags, int world, int step) {
+  const int p = threadIdx.x;
+  if (p >= world) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(my_flags + 16 + p) < step)
+    if (clock64() - t0 > 20000000000LL) __trap();
+}
+
 }  // namespace
+
+int launch_peer_push(const float* src, float* const* dsts, float* const* flag_ptrs, long long n_floats, int world, int rank,
+                     int step, int ctas, cudaStream_t st) {
+  if (world < 1 || world > kMaxPeers || (n_floats & 3)) return -1;
+  PushArgs a;
+  a.src = src; a.n_vec = n_floats / 4; a.world = world; a.rank = rank; a.step = step;
+  for (int d = 0; d < world; ++d) { a.dst[d] = dsts[d]; a.flags[d] = reinterpret_cast<int*>(flag_ptrs[d]); }
+  peer_push_kernel<<<ctas, 256, 0, st>>>(a);
+  peer_wait_pushed_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const int*>(flag_ptrs[rank]), world, step);
+  return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
 
 int launch_peer_barrier(float* const* flag_ptrs, int world, int rank, int epoch, cudaStream_t st) {
   if (world < 1 || world > kMaxPeers) return -1;

@@ -38,4 +38,8 @@ void decout_free_maps(DecOutMaps*);
 int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int n, cudaStream_t st);
 // signal + wait kernels of the peer-memory barrier (flag_ptrs[r] = rank r's flag array, int[8])
 int launch_peer_barrier(float* const* flag_ptrs, int world, int rank, int epoch, cudaStream_t st);
+// pipelined all-gather: copy this rank's decoded shard (src, n_floats) into every peer's gather buffer from a small
+// side-stream kernel + free/pushed flag handshake (see decout_tc.cu); returns after enqueueing push + wait kernels
+int launch_peer_push(const float* src, float* const* dsts, float* const* flag_ptrs, long long n_floats, int world, int rank,
+                     int step, int ctas, cudaStream_t st);
 }  // namespace ian

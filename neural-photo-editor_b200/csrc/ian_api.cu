@@ -173,6 +173,13 @@ struct ian_handle {
   float* gpeer_buf[8] = {nullptr};             // base of every rank's allocation (peer-mapped)
   bool gconnected = false;
   float** gather_dsts = nullptr;               // non-null only inside ian_reconstruct_gather_dev
+  int gather_ndst = 0;
+  // pipelined gather (ian_reconstruct_gather_async_dev): side stream + per-half events
+  cudaStream_t push_stream = nullptr;
+  cudaEvent_t g_comp[2] = {nullptr, nullptr}, g_done[2] = {nullptr, nullptr};
+  bool g_done_valid[2] = {false, false};
+  int g_last = -1;                             // buffer half of the most recent async step
+  int push_ctas = 16;
   long long tickets = 0;
   struct Ticket { int id = -1, n = 0, slot = 0; };
   Ticket inflight[2];          // the two most recent pipelined requests (ian_reconstruct_submit)
@@ -678,7 +685,7 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   ScopedTimer tm(h, T_DEC_OUT, st);
   if (h->path == IAN_PATH_TC) {
     float* one[1] = {xhat};
-    LAUNCH_TRY(h, launch_dec_out_tc(pl->decout_maps, h->gather_dsts ? h->gather_dsts : one, h->gather_dsts ? h->gw : 1, pl->n, st));
+    LAUNCH_TRY(h, launch_dec_out_tc(pl->decout_maps, h->gather_dsts ? h->gather_dsts : one, h->gather_dsts ? h->gather_ndst : 1, pl->n, st));
   }
   else
     LAUNCH_TRY(h, launch_dec_out(pl->h3.p, pl->h3.plane, h->decout_wt, xhat, pl->n, st));
@@ -1321,6 +1328,8 @@ int ian_destroy(ian_handle* h) {
   cudaFree(h->conv1_tc_wt); if (h->conv1_maps) conv1_free_maps(h->conv1_maps);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  if (h->push_stream) { cudaStreamSynchronize(h->push_stream); cudaStreamDestroy(h->push_stream); }
+  for (int b = 0; b < 2; ++b) { if (h->g_comp[b]) cudaEventDestroy(h->g_comp[b]); if (h->g_done[b]) cudaEventDestroy(h->g_done[b]); }
   for (int r = 0; r < h->gw; ++r) if (r != h->grank && h->gpeer_buf[r]) cudaIpcCloseMemHandle(h->gpeer_buf[r]);
   cudaFree(h->gbuf);
   for (void* p : h->host_allocs) cudaFreeHost(p);
@@ -1709,7 +1718,7 @@ int ian_gather_create(ian_handle* h, int world, int rank, int n_local, void* ipc
   if (!h || !ipc_handle_out) return fail(h, IAN_ERR_INVALID, "NULL argument");
   if (!h->finalized) return fail(h, IAN_ERR_STATE, "ian_finalize() has not been called");
   if (h->model_kind != IAN_MODEL_SIMPLE) return fail(h, IAN_ERR_UNSUPPORTED, "the fused gather is wired into the IAN_simple dec_out kernel");
-  if (world < 1 || world > 8 || rank < 0 || rank >= world || n_local < 1 || n_local > h->max_chunk)
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || n_local < 1 || n_local > 65536)
     return fail(h, IAN_ERR_INVALID, "bad world/rank/n_local (%d,%d,%d)", world, rank, n_local);
   if (h->gbuf) return fail(h, IAN_ERR_STATE, "gather buffers already created");
   DeviceGuard dg(h->device);
@@ -1737,33 +1746,103 @@ int ian_gather_connect(ian_handle* h, const void* all_handles) {
   return IAN_OK;
 }
 
-int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out, float** gathered_out, void* stream) {
-  int rc = check_ready(h, n_local, x, gathered_out);
+namespace {
+struct GatherSlots { float* dsts[8]; float* flags[8]; size_t half, mine; };
+GatherSlots gather_slots(const ian_handle* h) {
+  GatherSlots g;
+  g.half = (size_t)h->gw * h->gn * 12288;                         // floats per gather buffer
+  g.mine = (size_t)h->grank * h->gn * 12288;
+  for (int r = 0; r < h->gw; ++r) {
+    g.dsts[r] = h->gpeer_buf[r] + (size_t)h->gcur * g.half + g.mine;   // my shard's slot in rank r's current buffer
+    g.flags[r] = h->gpeer_buf[r] + 2 * g.half;                    // rank r's flag block (64 ints) after its buffers
+  }
+  return g;
+}
+
+int check_gather_ready(ian_handle* h, const float* x, int n_local) {
+  int rc = check_ready(h, n_local, x, x);
   if (rc != IAN_OK) return rc;
   if (!h->gconnected) return fail(h, IAN_ERR_STATE, "ian_gather_connect() has not been called");
   if (n_local != h->gn) return fail(h, IAN_ERR_INVALID, "n_local %d differs from the %d the gather buffers were sized for", n_local, h->gn);
   if (h->path != IAN_PATH_TC) return fail(h, IAN_ERR_UNSUPPORTED, "fused gather runs on the tensor-core path");
+  return IAN_OK;
+}
+
+// encode -> decode of the local shard (in <= 512-image chunks), dec_out storing into `ndst` destination bases
+int run_shard_into(ian_handle* h, const float* x, int n_local, float* z_out, float* const* bases, int ndst, cudaStream_t st) {
+  return for_chunks(h, n_local, [&](Plan* pl, int off, int) {
+    float* dsts[8];
+    for (int r = 0; r < ndst; ++r) dsts[r] = bases[r] + (size_t)off * 12288;
+    int rc = run_encode(h, pl, x + (size_t)off * 12288, nullptr, z_out ? z_out + (size_t)off * 100 : pl->z, st);
+    if (rc != IAN_OK) return rc;
+    h->gather_dsts = dsts; h->gather_ndst = ndst;
+    rc = run_decode_from_planes(h, pl, nullptr, st);
+    h->gather_dsts = nullptr; h->gather_ndst = 0;
+    return rc;
+  });
+}
+}  // namespace
+
+int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float* z_out, float** gathered_out, void* stream) {
+  if (!gathered_out) return fail(h, IAN_ERR_INVALID, "gathered_out is NULL");
+  int rc = check_gather_ready(h, x, n_local);
+  if (rc != IAN_OK) return rc;
   DeviceGuard dg(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  Plan* pl = nullptr;
-  if ((rc = get_plan(h, n_local, &pl)) != IAN_OK) return rc;
-  const size_t half = (size_t)h->gw * h->gn * 12288;             // floats per gather buffer
-  const size_t mine = (size_t)h->grank * h->gn * 12288;
-  float* dsts[8];
-  float* flags[8];
-  for (int r = 0; r < h->gw; ++r) {
-    dsts[r] = h->gpeer_buf[r] + (size_t)h->gcur * half + mine;    // my shard's slot in rank r's current buffer
-    flags[r] = h->gpeer_buf[r] + 2 * half;                        // rank r's flag array (int[8]) after its buffers
+  if (h->g_done_valid[h->gcur]) {                                  // an earlier pipelined step still owns this half
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_done[h->gcur], 0));
+    h->g_done_valid[h->gcur] = false;
   }
-  if ((rc = run_encode(h, pl, x, nullptr, z_out ? z_out : pl->z, st)) != IAN_OK) return rc;
-  h->gather_dsts = dsts;
-  rc = run_decode_from_planes(h, pl, nullptr, st);
-  h->gather_dsts = nullptr;
-  if (rc != IAN_OK) return rc;
+  GatherSlots g = gather_slots(h);
+  if ((rc = run_shard_into(h, x, n_local, z_out, g.dsts, h->gw, st)) != IAN_OK) return rc;   // peer stores from dec_out
   h->gepoch += 1;
-  LAUNCH_TRY(h, launch_peer_barrier(flags, h->gw, h->grank, h->gepoch, st));
-  *gathered_out = h->gbuf + (size_t)h->gcur * half;
+  LAUNCH_TRY(h, launch_peer_barrier(g.flags, h->gw, h->grank, h->gepoch, st));
+  *gathered_out = h->gbuf + (size_t)h->gcur * g.half;
   h->gcur ^= 1;
+  h->g_last = -1;
+  return IAN_OK;
+}
+
+// Pipelined form: the shard is decoded into this rank's own buffer on `stream`; a small copy kernel on a side stream
+// then pushes it to every peer while the caller's NEXT step computes.  ian_gather_wait_dev makes `stream` wait for the
+// most recent step's gather and returns its buffer.
+int ian_reconstruct_gather_async_dev(ian_handle* h, const float* x, int n_local, float* z_out, void* stream) {
+  int rc = check_gather_ready(h, x, n_local);
+  if (rc != IAN_OK) return rc;
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (!h->push_stream) {
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->g_comp[b], cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventCreateWithFlags(&h->g_done[b], cudaEventDisableTiming));
+    }
+    if (const char* c = getenv("IAN_PUSH_CTAS")) { int v = atoi(c); if (v >= 1 && v <= 148) h->push_ctas = v; }
+  }
+  const int half_id = h->gcur;
+  if (h->g_done_valid[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_done[half_id], 0));   // push of step t-2 has read this half
+  GatherSlots g = gather_slots(h);
+  float* local[1] = {g.dsts[h->grank]};
+  if ((rc = run_shard_into(h, x, n_local, z_out, local, 1, st)) != IAN_OK) return rc;
+  CUDA_TRY(h, cudaEventRecord(h->g_comp[half_id], st));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->g_comp[half_id], 0));
+  h->gepoch += 1;
+  LAUNCH_TRY(h, launch_peer_push(g.dsts[h->grank], g.dsts, g.flags, (long long)n_local * 12288, h->gw, h->grank, h->gepoch,
+                                 h->push_ctas, h->push_stream));
+  CUDA_TRY(h, cudaEventRecord(h->g_done[half_id], h->push_stream));
+  h->g_done_valid[half_id] = true;
+  h->g_last = half_id;
+  h->gcur ^= 1;
+  return IAN_OK;
+}
+
+int ian_gather_wait_dev(ian_handle* h, float** gathered_out, void* stream) {
+  if (!h || !gathered_out) return fail(h, IAN_ERR_INVALID, "NULL argument");
+  if (h->g_last < 0) return fail(h, IAN_ERR_STATE, "no pipelined gather step is outstanding");
+  DeviceGuard dg(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_done[h->g_last], 0));
+  *gathered_out = h->gbuf + (size_t)h->g_last * ((size_t)h->gw * h->gn * 12288);
   return IAN_OK;
 }
 

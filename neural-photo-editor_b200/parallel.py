@@ -46,3 +46,12 @@ def sharded_reconstruct(reconstruct_fn, x, group=None):
     rank = dist.get_rank(group)
     lo, hi = shard_bounds(x.shape[0], rank, world)
     return gather_images(reconstruct_fn(x[lo:hi]), x.shape[0], group)
+
+
+def as_cuda_tensor(ptr: int, shape, device):
+    """zero-copy torch view of a float32 device buffer owned by the library (the gather buffer)."""
+    import torch
+
+    class _Ptr:
+        __cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Ptr(), device=device)

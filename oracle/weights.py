@@ -139,3 +139,18 @@ def make_v1_weights(seed=0, w_std=0.02):
             std = 0.05 if (name.endswith("W") and not name.endswith(".W")) else (0.1 if name == "l_dec_fc2.W" else w_std)
             P[name] = rng.normal(0, std, shp).astype(np.float32)
     return P
+
+
+# ---- BASELINE config 4 inputs: the latent-brush edit loop -----------------------------------
+def config4_inputs(n=128):
+    """z ~ N(0,1) seed 2; per-sample brush boxes by NPE's law (NPE.py:143-156: side w in 1..17, origin uniform so that
+    the box stays inside the 64x64 frame) and target colours U(-1,1)^3, seed 3.  Returns z (n,100) f32,
+    boxes (n,4) int32 [c1,r1,c2,r2], rgb (n,3) f32."""
+    z = np.random.default_rng(2).standard_normal((n, 100)).astype(np.float32)
+    r3 = np.random.default_rng(3)
+    side = r3.integers(1, 18, n)
+    c1 = np.array([r3.integers(0, 64 - s + 1) for s in side])
+    r1 = np.array([r3.integers(0, 64 - s + 1) for s in side])
+    boxes = np.stack([c1, r1, c1 + side, r1 + side], 1).astype(np.int32)
+    rgb = r3.uniform(-1, 1, (n, 3)).astype(np.float32)
+    return z, boxes, rgb
