@@ -161,6 +161,10 @@ struct ian_handle {
   int* sk_flags = nullptr;
   int sk_epoch = 0;
   bool streamk = true;
+  bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
+  bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
+  int tc2_min_tiles = 74;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN)
+  std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
   bool graphs = true;          // replay small-batch host calls as CUDA graphs (IAN_GRAPHS=0 turns it off)
   bool capturing = false;
   bool finalized = false;
@@ -252,6 +256,7 @@ struct Plan {
   float *z0 = nullptr, *ha = nullptr, *rg = nullptr, *tt = nullptr;   // tt: head tap table [n][198][4096]
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
+  Tc2Maps* maps2[L_COUNT] = {nullptr};   // CTA-pair kernel (only for layers with enough whole tiles; see build_pair_maps)
   DecOutMaps* decout_maps = nullptr;
   // pipelined host API: double-buffered boundary tensors + events (allocated on first use)
   float *sx[2] = {nullptr, nullptr}, *sz[2] = {nullptr, nullptr}, *sxh[2] = {nullptr, nullptr};
@@ -414,12 +419,28 @@ int alloc_splitk_workspace(ian_handle* h, Plan* pl) {
   return IAN_OK;
 }
 
+// A layer moves to the CTA-pair kernel when it runs whole tiles (no split-K, no channel-major output), its channel
+// counts fit the 256 x 128 pair tile and it has at least tc2_min_tiles pair-tiles (one per SM pair).
+int build_pair_maps(ian_handle* h, Plan* pl, int l) {
+  const TapGemm& g = pl->g[l];
+  if (!h->tc2 || g.ksplit != 1 || g.out_f32_t || g.Cout % 128 || g.Cin % 64) return IAN_OK;
+  if (!h->tc2_skip.empty() && h->tc2_skip.find(std::string(",") + kLayerNames[l] + ",") != std::string::npos) return IAN_OK;
+  char err[256] = {0};
+  Tc2Maps* m = tc2_build_maps(g, err, sizeof(err));
+  if (!m) return fail(h, IAN_ERR_CUDA, "layer %s (pair kernel): %s", kLayerNames[l], err);
+  if (tc2_pair_tiles(g, m) < h->tc2_min_tiles) { tc2_free_maps(m); return IAN_OK; }
+  pl->maps2[l] = m;
+  return IAN_OK;
+}
+
 int finish_maps(ian_handle* h, Plan* pl, std::initializer_list<int> layers) {
   for (int l : layers) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(pl->g[l], err, sizeof(err));
     if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
-    if (pl->g[l].ksplit == 0) pl->g[l].ksplit = choose_ksplit(pl->g[l]);
+    if (pl->g[l].ksplit == 0) pl->g[l].ksplit = h->splitk ? choose_ksplit(pl->g[l]) : 1;
+    int rc = build_pair_maps(h, pl, l);
+    if (rc != IAN_OK) return rc;
   }
   return alloc_splitk_workspace(h, pl);
 }
@@ -563,7 +584,8 @@ int build_plan(ian_handle* h, int n, Plan** out) {
     char err[256] = {0};
     pl->maps[l] = tc_build_maps(g[l], err, sizeof(err));
     if (!pl->maps[l]) return fail(h, IAN_ERR_CUDA, "layer %s: %s", kLayerNames[l], err);
-    if (g[l].ksplit == 0) g[l].ksplit = choose_ksplit(g[l]);
+    if (g[l].ksplit == 0) g[l].ksplit = h->splitk ? choose_ksplit(g[l]) : 1;
+    if ((rc = build_pair_maps(h, pl, l)) != IAN_OK) return rc;
   }
   if ((rc = alloc_splitk_workspace(h, pl)) != IAN_OK) return rc;
   {
@@ -583,6 +605,7 @@ void free_plan(Plan* pl) {
     if (pl->ev_d2h[s]) cudaEventDestroy(pl->ev_d2h[s]);
   }
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps[l]) tc_free_maps(pl->maps[l]);
+  for (int l = 0; l < L_COUNT; ++l) if (pl->maps2[l]) tc2_free_maps(pl->maps2[l]);
   if (pl->decout_maps) decout_free_maps(pl->decout_maps);
   for (auto& gs : pl->graph) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   delete pl;
@@ -631,7 +654,8 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
   } else {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
-    LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
+    if (pl->maps2[l]) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
+    else LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
     if (g.ksplit > 1) LAUNCH_TRY(h, launch_splitk_finalize(g, st));
   }
@@ -1216,6 +1240,10 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   if (const char* c = getenv("IAN_CHUNK")) { int v = atoi(c); if (v > 0) h->max_chunk = v > 4096 ? 4096 : v; }
   if (const char* c = getenv("IAN_PATH")) { if (!strcmp(c, "simt")) h->path = IAN_PATH_SIMT; }
   if (const char* c = getenv("IAN_STREAMK")) h->streamk = atoi(c) != 0;
+  if (const char* c = getenv("IAN_SPLITK")) h->splitk = atoi(c) != 0;
+  if (const char* c = getenv("IAN_TC2")) h->tc2 = atoi(c) != 0;
+  if (const char* c = getenv("IAN_TC2_MIN")) { int v = atoi(c); if (v > 0) h->tc2_min_tiles = v; }
+  if (const char* c = getenv("IAN_TC2_SKIP")) h->tc2_skip = std::string(",") + c + ",";
   if (const char* c = getenv("IAN_GRAPHS")) h->graphs = atoi(c) != 0;
   *out = h;
   return IAN_OK;

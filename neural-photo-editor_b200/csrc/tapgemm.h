@@ -134,6 +134,13 @@ TcMaps* tc_build_maps(const TapGemm& g, char* err, int errlen);
 void tc_free_maps(TcMaps*);
 int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st);
 int launch_splitk_finalize(const TapGemm& g, cudaStream_t st);
+// CTA-pair path (tapgemm_tc2.cu): tcgen05.mma.cta_group::2, 256 x 128 tiles, double-buffered accumulators in float32
+// mode; whole tiles only (ksplit == 1, no channel-major output)
+struct Tc2Maps;
+Tc2Maps* tc2_build_maps(const TapGemm& g, char* err, int errlen);
+void tc2_free_maps(Tc2Maps*);
+long long tc2_pair_tiles(const TapGemm& g, const Tc2Maps* maps);
+int launch_tapgemm_tc2(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st);
 int tc_tile_width(const TcMaps* maps);
 int tc_num_sms();
 size_t tc_sk_workspace_floats();   // per handle: 148 slots x 128 x 256 fp32

@@ -164,3 +164,32 @@ def test_ianv1_golden(npe, gold_v1, path):
             assert err.max() <= 0.2 and err.mean() <= 8e-3
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("which", ["full", "v1"])
+def test_pair_kernel_on_the_flow_models(npe, which, monkeypatch):
+    """the CTA-pair tap-GEMM on the IAN.py / IANv1.py graphs (MDC taps, residual + raw-output epilogue of the MDBLOCKs),
+    float32 split and single-pass bf16 mode, against the one-CTA kernel on the same schedule."""
+    from oracle import weights as ow
+    P = (ow.make_v1_weights if which == "v1" else ow.make_full_weights)(0)
+    cfg = "IANv1.py" if which == "v1" else "IAN.py"
+    for k, v in (("IAN_SPLITK", "0"), ("IAN_STREAMK", "0"), ("IAN_GRAPHS", "0")):
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("IAN_TC2", "0")
+    one = npe.IAN(cfg, True, weights=P)
+    monkeypatch.setenv("IAN_TC2", "1")
+    monkeypatch.setenv("IAN_TC2_MIN", "1")
+    pair = npe.IAN(cfg, True, weights=P)
+    rng = np.random.default_rng(43)
+    try:
+        for prec, tol in (("fp32", 1e-6), ("bf16", 1e-6)):
+            one.set_precision(prec)
+            pair.set_precision(prec)
+            for n in (2, 5):
+                x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
+                xa, za = one.reconstruct(x, return_z=True)
+                xb, zb = pair.reconstruct(x, return_z=True)
+                assert np.abs(za - zb).max() <= tol and np.abs(xa - xb).max() <= tol, (prec, n)
+    finally:
+        one.close()
+        pair.close()

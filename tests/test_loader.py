@@ -104,8 +104,10 @@ def test_uploaded_made_weights_are_w_times_mask_bit_for_bit(npe, which):
         m._check(m._lib.ian_debug_made_weights(m._h, got.ctypes.data_as(C.POINTER(C.c_float))))
         for a, net in enumerate(("l_IAF_mu", "l_IAF_ls")):
             for b, (sub, key) in enumerate((("_input", "mask_input"), ("_output_W", "mask_output_W"), ("_output_D", "mask_output_D"))):
-                want = P[net + sub + ".W"] * ref[key].astype(np.float32)
-                assert np.array_equal(got[a, b].view(np.uint32), want.view(np.uint32)), (net, sub)
+                keep = ref[key] != 0
+                W = P[net + sub + ".W"]
+                assert np.array_equal(got[a, b].view(np.uint32)[keep], W.view(np.uint32)[keep]), (net, sub)   # kept weights: same bits
+                assert not got[a, b][~keep].any(), (net, sub)                                              # masked weights: exactly zero
     finally:
         m.close()
 
