@@ -20,7 +20,7 @@ int launch_npe_blend(const float* xhat, const uint8_t* recon, const float* error
 // full IAN: MADE+IAF latent flow and the autoregressive RGB-Beta head
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st);
-int launch_head_gather(const float* tt, const int* taps, int ntaps, float* ha, int n, cudaStream_t st);
+int launch_head_gather(const float* tt, int tt_is_bf16, const int* taps, int ntaps, float* ha, int n, cudaStream_t st);
 int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
                          float* xhat, int n, cudaStream_t st);
 // enc_conv1 on the tensor-core path (conv1_tc.cu): thread-built im2col tile + tcgen05

@@ -362,7 +362,14 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // tt: tap table of one dense GEMM (no shifts), tile-blocked: tt[(n*32 + p/2)][t*6+f][(p%2)*64 + q] =
 //     sum_c h[n,p,q,c] * Wc[t][f][c]       (a tile = 2 image rows, see TapGemm::out_f32_t)
 // ha[pix][f] = sum_t tt[..pix + (dy_t, dx_t)..][t*6+f]  -- the 33 dilated taps become 33 coalesced shifted reads.
-__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ tt, const int* __restrict__ taps, int ntaps,
+template <typename T> __device__ __forceinline__ float tt_load(const T* p);
+template <> __device__ __forceinline__ float tt_load<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float tt_load<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(__ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) head_gather_kernel(const T* __restrict__ tt, const int* __restrict__ taps, int ntaps,
                                                           float* __restrict__ ha, int n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
@@ -373,9 +380,9 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restric
   for (int t = 0; t < ntaps; ++t) {
     const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
     if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
-    const float* src = tt + ((img * 32 + (pp >> 1)) * ncol + t * 6) * 128 + (pp & 1) * 64 + qq;
+    const T* src = tt + ((img * 32 + (pp >> 1)) * ncol + t * 6) * 128 + (pp & 1) * 64 + qq;
 #pragma unroll
-    for (int f = 0; f < 6; ++f) a[f] += src[f * 128];
+    for (int f = 0; f < 6; ++f) a[f] += tt_load<T>(src + f * 128);
   }
   float* o = ha + i * 16;
   *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
@@ -556,9 +563,12 @@ int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z,
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_head_gather(const float* tt, const int* taps, int ntaps, float* ha, int n, cudaStream_t st) {
+int launch_head_gather(const float* tt, int tt_is_bf16, const int* taps, int ntaps, float* ha, int n, cudaStream_t st) {
   const long long npix = (long long)n * 4096;
-  head_gather_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(tt, taps, ntaps, ha, n);
+  if (tt_is_bf16)
+    head_gather_kernel<__nv_bfloat16><<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(tt), taps, ntaps, ha, n);
+  else
+    head_gather_kernel<float><<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(tt, taps, ntaps, ha, n);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

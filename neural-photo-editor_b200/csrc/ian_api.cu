@@ -638,6 +638,7 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
   TapGemm g = pl->g[l];
   if (g.ksplit < 1) return fail(h, IAN_ERR_INVALID, "layer %s is not part of this plan", kLayerNames[l]);
   g.passes = h->passes;
+  g.out_t_bf16 = (g.out_f32_t && h->passes == 1) ? 1 : 0;   // bf16 mode: the head's tap table travels as bf16
   g.sk_ws = (h->streamk && !h->capturing) ? h->sk_ws : nullptr;   // the stream-K epoch is a kernel argument: not replayable
   g.sk_flags = h->sk_flags;
   g.sk_epoch = ++h->sk_epoch;
@@ -654,7 +655,10 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
   } else {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
-    if (pl->maps2[l]) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
+    // pair kernel: float32-split mode always (256 x 128 tiles); bf16 mode only with 256 x 256 tiles (Cout % 256 == 0) --
+    // measured: 256 x 128 single-pass tiles lose to the one-CTA kernel's 128 x 256 / paired-M tiles (smem port bound)
+    const bool pair = pl->maps2[l] && (h->passes == 3 || (g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
+    if (pair) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
     else LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
     if (g.ksplit > 1) LAUNCH_TRY(h, launch_splitk_finalize(g, st));
@@ -693,14 +697,14 @@ int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st
   if (h->model_kind == IAN_MODEL_V1) {
     for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4, F_HEAD})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
+    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
     LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
     return IAN_OK;
   }
   if (h->model_kind == IAN_MODEL_FULL) {
     for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
+    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
     LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
     return IAN_OK;
   }

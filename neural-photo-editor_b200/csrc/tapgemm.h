@@ -97,6 +97,7 @@ struct TapGemm {
   // tile and tile order follow tile_shape() below.  Used for the RGB-Beta head's tap table.
   float* out_f32_t;
   int cout_real;
+  int out_t_bf16;               // 1: the same table stored as bf16 (single-pass bf16 mode: halves the head's HBM round trip)
   int passes;                   // 3 = float32 via bf16 hi|lo split (default), 1 = plain bf16 (hi planes only)
   // stream-K (see WorkIter in tapgemm_tc.cu): per-CTA partial-sum slots [cta][8][32][BN/2] fp32, arrival flags
   // [cta][8] holding the epoch of the launch that wrote them; sk_ws == nullptr selects whole-tile scheduling

@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
       const int ml = ((n % Nt) * Ht + p % Ht) * Wt + q % Wt;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (co + j < g.cout_real) g.out_f32_t[(mtile * g.cout_real + co + j) * 128 + ml] = f4[j];
+        if (co + j < g.cout_real) {
+          const long long ti = (mtile * g.cout_real + co + j) * 128 + ml;
+          if (g.out_t_bf16) reinterpret_cast<__nv_bfloat16*>(g.out_f32_t)[ti] = __float2bfloat16_rn(f4[j]);
+          else g.out_f32_t[ti] = f4[j];
+        }
     }
   }
 }

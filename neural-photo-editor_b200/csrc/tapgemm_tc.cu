@@ -450,11 +450,19 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
               }
             }
             if (g.out) store_split<CH, PASSES>(g.out + off, g.out_plane, v);
-            if (g.out_f32_t) {                           // tile-blocked channel-major fp32: [m-tile][co][128 rows]
-              float* ot = g.out_f32_t + ((long long)wi.mtile[tj] * g.cout_real + co) * BM + ml;
+            if (g.out_f32_t) {                           // tile-blocked channel-major table: [m-tile][co][128 rows]
+              const long long tbase = ((long long)wi.mtile[tj] * g.cout_real + co) * BM + ml;
+              if (g.out_t_bf16) {
+                __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(g.out_f32_t) + tbase;
 #pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (co + j < g.cout_real) ot[j * BM] = v[j];   // a warp writes 128 contiguous bytes per column
+                for (int j = 0; j < CH; ++j)
+                  if (co + j < g.cout_real) ot[j * BM] = __float2bfloat16_rn(v[j]);   // a warp writes 64 contiguous bytes per column
+              } else {
+                float* ot = g.out_f32_t + tbase;
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (co + j < g.cout_real) ot[j * BM] = v[j];   // a warp writes 128 contiguous bytes per column
+              }
             }
             if (g.out_f32) {
               float4* of = reinterpret_cast<float4*>(g.out_f32 + off);

@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "tapgemm.h"
 #include "tc_ptx.cuh"
@@ -30,10 +31,12 @@ namespace ian {
 
 struct Tc2Maps {
   CUtensorMap a[4];     // activation views, box = {64 ch, Wt, Ht, Nt, 2 planes}
-  CUtensorMap b;        // weights, box = {64 ch, BN/2, 2 planes}
+  CUtensorMap b;        // weights, box = {64 ch, 64 rows (half of BN = 128), 2 planes}
   CUtensorMap a1[4];    // hi plane only (bf16 mode)
-  CUtensorMap b1;
-  int Wt, Ht, Nt, BN;
+  CUtensorMap b1;       // bf16 mode: box = {64 ch, BN1/2 rows, 1 plane}
+  int Wt, Ht, Nt, BN;   // BN: float32-split mode tile width (128: main|cross x 2 buffers = 512 TMEM columns)
+  int BN1;              // bf16 mode tile width: 256 when Cout % 256 == 0 (one accumulator: 2 x 256 columns), else 128
+  mutable int sk_choice[2];   // cached stream-K decision per mode (float32-split, bf16): -1 unknown, 0 whole tiles, 1 stream-K
 };
 
 namespace {
@@ -136,20 +139,20 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16* dst, long long plane
 
 // work item of a PAIR: (phase | n-tile | pair of m-tiles); this CTA's m-tile is 2*mp + rank
 struct PairWork {
-  int phase, co0, iters;
+  int phase, co0, it0, it1;
   int n0, p0, q0, mtile;
+  // stream-K: 0 = whole tile; 1 = contributor (a later part of a tile: raw sums -> this CTA's workspace slot);
+  // 2 = finisher (the first part of a tile cut by a pair boundary: adds the parts of pairs pair+1 .. sk_last, in order)
+  int sk_role, sk_last;
 };
 
+// pair-tile index within a phase -> this CTA's tile
 template <int BN>
-__device__ __forceinline__ PairWork decode_pair_work(const TapGemm& g, const Tc2Maps& maps, int w, int rank) {
-  PairWork wi;
+__device__ __forceinline__ void decode_tile(const TapGemm& g, const Tc2Maps& maps, int phase, int r, int rank, PairWork& wi) {
   const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
   const int tiles_m = tiles_q * tiles_p * ((g.n_img + maps.Nt - 1) / maps.Nt);
   const int pairs_m = (tiles_m + 1) / 2;
-  const int tiles_n = g.Cout / BN;
-  const int per_phase = pairs_m * tiles_n;
-  wi.phase = w / per_phase;
-  int r = w % per_phase;
+  wi.phase = phase;
   const int mp = r % pairs_m;
   const int nt = r / pairs_m;
   int mt = 2 * mp + rank;
@@ -162,11 +165,63 @@ __device__ __forceinline__ PairWork decode_pair_work(const TapGemm& g, const Tc2
     wi.n0 = mt * maps.Nt; wi.p0 = pb * maps.Ht; wi.q0 = qb * maps.Wt;
   }
   wi.co0 = nt * BN;
-  wi.iters = g.phase[wi.phase].ntaps * (g.Cin / BK);
-  return wi;
 }
 
-template <int BN, int PASSES>
+// Work iteration of one pair.  SK = false: whole pair-tiles, w = pair + i * npairs (longest phases first).
+// SK = true (stream-K, same ordered atomic-free scheme as tapgemm_tc.cu's WorkIter): the launch is ONE linear space of T
+// K steps over (phase | n-tile | m-pair | K step) and pair c owns steps [T*c/G, T*(c+1)/G): every SM pair gets the same
+// tensor work however the tile count divides by 74 and however unequal the phases are.  A tile cut by a pair boundary is
+// finished by the pair holding its FIRST K steps (reached at the END of its range) after the pairs holding the later
+// steps (which they run FIRST) have published raw partial sums + a release flag.  Both CTAs of a pair walk the same
+// schedule; CTA rank r exchanges partial sums with CTA rank r of the neighbouring pairs (same 128 rows of the tile).
+template <int BN, bool SK>
+struct PairIter {
+  int w, total, stride, per_phase;                                  // !SK
+  int T, G, cur, end;                                               // SK
+  int pair, nchunk;
+  __device__ __forceinline__ int iters_of(const TapGemm& g, int ph) const { return g.phase[ph].ntaps * nchunk; }
+  __device__ __forceinline__ int boundary(int c) const { return (int)((long long)T * c / G); }
+  __device__ __forceinline__ int owner(int gi) const {
+    int c = (int)((long long)gi * G / T);
+    while (c + 1 < G && boundary(c + 1) <= gi) ++c;
+    while (c > 0 && boundary(c) > gi) --c;
+    return c;
+  }
+  __device__ __forceinline__ void init(const TapGemm& g, const Tc2Maps& maps, int total_work, int pair_, int npairs) {
+    pair = pair_;
+    const int tiles_q = g.Wg / maps.Wt, tiles_p = g.Hg / maps.Ht;
+    const int tiles_m = tiles_q * tiles_p * ((g.n_img + maps.Nt - 1) / maps.Nt);
+    per_phase = ((tiles_m + 1) / 2) * (g.Cout / BN);
+    nchunk = g.Cin / BK;
+    if (!SK) { w = pair; total = total_work; stride = npairs; return; }
+    T = total_work; G = npairs;
+    cur = boundary(pair); end = boundary(pair + 1);
+  }
+  __device__ __forceinline__ bool next(const TapGemm& g, const Tc2Maps& maps, int rank, PairWork& wi) {
+    if (!SK) {
+      if (w >= total) return false;
+      decode_tile<BN>(g, maps, w / per_phase, w % per_phase, rank, wi);
+      wi.it0 = 0; wi.it1 = iters_of(g, wi.phase); wi.sk_role = 0; wi.sk_last = 0;
+      w += stride;
+      return true;
+    }
+    if (cur >= end) return false;
+    int gi = cur, ph = 0, phase_start = 0;
+    while (ph + 1 < g.nphase && gi >= phase_start + per_phase * iters_of(g, ph)) { phase_start += per_phase * iters_of(g, ph); ++ph; }
+    const int ip = iters_of(g, ph);
+    const int tile = (gi - phase_start) / ip, it = (gi - phase_start) % ip;
+    int len = ip - it;
+    if (len > end - gi) len = end - gi;
+    decode_tile<BN>(g, maps, ph, tile, rank, wi);
+    wi.it0 = it; wi.it1 = it + len;
+    wi.sk_role = it > 0 ? 1 : (len < ip ? 2 : 0);
+    wi.sk_last = wi.sk_role == 2 ? owner(phase_start + tile * ip + ip - 1) : 0;
+    cur = gi + len;
+    return true;
+  }
+};
+
+template <int BN, int PASSES, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc2Maps maps, const int total_work) {
   using Cfg = Tc2Cfg<BN, PASSES>;
@@ -213,10 +268,12 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t i = 0;
-      for (int w = pair; w < total_work; w += npairs) {
-        const PairWork wi = decode_pair_work<BN>(g, maps, w, (int)rank);
+      PairIter<BN, SK> iter;
+      iter.init(g, maps, total_work, pair, npairs);
+      PairWork wi;
+      while (iter.next(g, maps, (int)rank, wi)) {
         const Phase ph = g.phase[wi.phase];
-        for (int it = 0; it < wi.iters; ++it, ++i) {
+        for (int it = wi.it0; it < wi.it1; ++it, ++i) {
           const int s = i % S;
           const uint32_t par = (i / S) & 1u;
           const Tap tap = g.taps[ph.tap_begin + it / nchunk];
@@ -237,13 +294,15 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_m256(BN);
       uint32_t i = 0, t = 0;
-      for (int w = pair; w < total_work; w += npairs, ++t) {
-        const PairWork wi = decode_pair_work<BN>(g, maps, w, 0);
+      PairIter<BN, SK> iter;
+      iter.init(g, maps, total_work, pair, npairs);
+      PairWork wi;
+      for (; iter.next(g, maps, 0, wi); ++t) {
         const uint32_t buf = t & 1u, use = t >> 1;
         const uint32_t acc_main = tmem_base + buf * Cfg::kAccCols, acc_cross = acc_main + BN;
         mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);    // both CTAs' epilogues have drained this buffer
         tc_fence_after();
-        for (int it = 0; it < wi.iters; ++it, ++i) {
+        for (int it = wi.it0; it < wi.it1; ++it, ++i) {
           const int s = i % S;
           const uint32_t par = (i / S) & 1u;
           mbar_wait(full_bar(s), par);                  // A and B halves of both CTAs have landed
@@ -254,7 +313,7 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ko = (uint64_t)(k * 2);      // 32 bytes per K=16 slice, in 16-byte units
-            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            const uint32_t acc = (it > wi.it0 || k > 0) ? 1u : 0u;
             umma2_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
             if (PASSES == 3) {
               umma2_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
@@ -282,8 +341,11 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
     const int nl = ml / (maps.Wt * maps.Ht);
     const uint32_t lead_tempty[2] = {mapa_u32(tempty_bar(0), 0), mapa_u32(tempty_bar(1), 0)};
     uint32_t t = 0;
-    for (int w = pair; w < total_work; w += npairs, ++t) {
-      const PairWork wi = decode_pair_work<BN>(g, maps, w, (int)rank);
+    const int my_cta = 2 * pair + (int)rank;            // workspace / flag slot of this CTA
+    PairIter<BN, SK> iter;
+    iter.init(g, maps, total_work, pair, npairs);
+    PairWork wi;
+    for (; iter.next(g, maps, (int)rank, wi); ++t) {
       const Phase ph = g.phase[wi.phase];
       const uint32_t buf = t & 1u, use = t >> 1;
       if (g.scale_pix_stride == 0) {                    // stage this tile's per-channel scale/shift while the MMAs run
@@ -297,6 +359,18 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
       }
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after();
+      if (SK && wi.sk_role == 2) {                      // finisher: the later parts were computed first; wait for them
+        for (int k = pair + 1 + lane; k <= wi.sk_last; k += 32) {
+          const int* fl = g.sk_flags + (2 * k + (int)rank) * kEpiWarps + ew;
+          const long long t0 = clock64();
+          int fv;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fv) : "l"(fl) : "memory");
+            if (clock64() - t0 > 4000000000LL) __trap();
+          } while (fv != g.sk_epoch);
+        }
+        __syncwarp();
+      }
       const int n = wi.n0 + nl, p = wi.p0 + hl, q = wi.q0 + wl;
       const bool valid = n < g.n_img;
       const int oh = p * g.osh + ph.oh0, ow = q * g.osw + ph.ow0;
@@ -327,6 +401,22 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
           __syncwarp();
           if (lane == 0) {
             if (rank == 0) mbar_arrive(tempty_bar(buf)); else mbar_arrive_cluster(lead_tempty[buf]);
+          }
+        }
+        if (SK && wi.sk_role == 1) {                     // contributor: raw partial sums -> this CTA's workspace slot
+          float4* wp = reinterpret_cast<float4*>(g.sk_ws + (((long long)my_cta * kEpiWarps + ew) * 32 + lane) * COLS_PER_WARP + cc);
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) __stcg(wp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          continue;
+        }
+        if (SK && wi.sk_role == 2) {                     // finisher: add the later parts, in pair order
+          for (int k = pair + 1; k <= wi.sk_last; ++k) {
+            const float4* rp = reinterpret_cast<const float4*>(g.sk_ws + (((long long)(2 * k + (int)rank) * kEpiWarps + ew) * 32 + lane) * COLS_PER_WARP + cc);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 a = __ldcg(rp + j);
+              v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+            }
           }
         }
         if (!valid) continue;
@@ -388,6 +478,14 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
           for (int j = 0; j < CH / 4; ++j) of[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
+      if (SK && wi.sk_role == 1) {                       // publish this warp's sub-block of partial sums
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          int* fl = g.sk_flags + my_cta * kEpiWarps + ew;
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl), "r"(g.sk_epoch) : "memory");
+        }
+      }
     }
   }
 
@@ -407,6 +505,8 @@ Tc2Maps* tc2_build_maps(const TapGemm& g, char* err, int errlen) {
   memset(m, 0, sizeof(*m));
   tile_shape(g.Hg, g.Wg, m->Wt, m->Ht, m->Nt);
   m->BN = 128;
+  m->BN1 = (g.Cout % 256 == 0) ? 256 : 128;
+  m->sk_choice[0] = m->sk_choice[1] = -1;
   if (g.Wg % m->Wt || g.Hg % m->Ht || m->Wt * m->Ht * m->Nt != BM) {
     snprintf(err, errlen, "M grid %dx%d does not tile into 128-row boxes", g.Hg, g.Wg);
     delete m; return nullptr;
@@ -447,6 +547,7 @@ Tc2Maps* tc2_build_maps(const TapGemm& g, char* err, int errlen) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete m; return nullptr; }
+    box[1] = (cuuint32_t)(m->BN1 / 2);
     box[2] = 1;
     r = enc(&m->b1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)g.b, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -458,31 +559,69 @@ Tc2Maps* tc2_build_maps(const TapGemm& g, char* err, int errlen) {
 void tc2_free_maps(Tc2Maps* m) { delete m; }
 
 // pair-tiles of this launch, and whether the pair kernel should take it (enough whole tiles to fill the 74 pairs twice)
-long long tc2_pair_tiles(const TapGemm& g, const Tc2Maps* maps) {
+static long long pair_tiles_bn(const TapGemm& g, const Tc2Maps* maps, int bn) {
   const int tiles_m = (g.Wg / maps->Wt) * (g.Hg / maps->Ht) * ((g.n_img + maps->Nt - 1) / maps->Nt);
-  return (long long)((tiles_m + 1) / 2) * (g.Cout / maps->BN) * g.nphase;
+  return (long long)((tiles_m + 1) / 2) * (g.Cout / bn) * g.nphase;
 }
+long long tc2_pair_tiles(const TapGemm& g, const Tc2Maps* maps) { return pair_tiles_bn(g, maps, maps->BN); }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, bool SK>
 static int launch_pair(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st) {
   using Cfg = Tc2Cfg<BN, PASSES>;
   static DeviceOnce attr_set;
   const int dev = cur_device();
   if (!attr_set.is_done(dev)) {
-    if (cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tapgemm_tc2_kernel<BN, PASSES, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
     attr_set.set_done(dev);
   }
-  const int total_work = (int)tc2_pair_tiles(g, maps);
+  const int tiles = (int)pair_tiles_bn(g, maps, BN);
   const int pairs_hw = tc_num_sms() / 2;
-  const int pairs = total_work < pairs_hw ? total_work : pairs_hw;
-  tapgemm_tc2_kernel<BN, PASSES><<<2 * pairs, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  int total_work = tiles, pairs = tiles < pairs_hw ? tiles : pairs_hw;
+  if (SK) {                                              // T K-steps, one pair per SM pair, every pair gets T/G of them
+    const int per_phase = tiles / g.nphase;
+    long long T = 0;
+    for (int p = 0; p < g.nphase; ++p) T += (long long)per_phase * g.phase[p].ntaps * (g.Cin / BK);
+    total_work = (int)T;
+    pairs = pairs_hw;
+  }
+  tapgemm_tc2_kernel<BN, PASSES, SK><<<2 * pairs, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+static bool want_streamk_uncached(const TapGemm& g, const Tc2Maps* maps, int bn);
+// stream-K pays one partial-sum round trip per pair boundary; it is used where the static whole-tile schedule would leave
+// >= 8 % of the pair-time idle (makespan test on the host, cached per layer).
+static bool want_streamk(const TapGemm& g, const Tc2Maps* maps, int bn) {
+  if (!g.sk_ws) return false;
+  int& cached = maps->sk_choice[g.passes == 1 ? 1 : 0];
+  if (cached >= 0) return cached == 1;
+  cached = want_streamk_uncached(g, maps, bn) ? 1 : 0;
+  return cached == 1;
+}
+static bool want_streamk_uncached(const TapGemm& g, const Tc2Maps* maps, int bn) {
+  const int tiles = (int)pair_tiles_bn(g, maps, bn);
+  const int G = tc_num_sms() / 2;
+  if (tiles < G / 2) return false;
+  const int per_phase = tiles / g.nphase;
+  long long T = 0, makespan = 0;
+  std::vector<long long> load(G, 0);
+  for (int w = 0; w < tiles; ++w) {
+    const long long it = (long long)g.phase[w / per_phase].ntaps * (g.Cin / BK);
+    load[w % G] += it;
+    T += it;
+  }
+  for (long long v : load) makespan = v > makespan ? v : makespan;
+  return makespan * G * 100 >= T * 108;
 }
 
 int launch_tapgemm_tc2(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st) {
   if (g.ksplit != 1 || g.out_f32_t) return -1;
-  return g.passes == 1 ? launch_pair<128, 1>(g, maps, st) : launch_pair<128, 3>(g, maps, st);
+  if (g.passes == 1) {
+    if (maps->BN1 != 256) return -1;                      // Cout = 128 in bf16 mode: one-CTA kernel
+    return want_streamk(g, maps, 256) ? launch_pair<256, 1, true>(g, maps, st) : launch_pair<256, 1, false>(g, maps, st);
+  }
+  return want_streamk(g, maps, 128) ? launch_pair<128, 3, true>(g, maps, st) : launch_pair<128, 3, false>(g, maps, st);
 }
 
 }  // namespace ian

@@ -370,8 +370,16 @@ def test_pair_kernel_equals_one_cta_kernel(npe, weights, monkeypatch):
     monkeypatch.setenv("IAN_TC2", "1")
     monkeypatch.setenv("IAN_TC2_MIN", "1")
     pair = npe.IAN("IAN_simple.py", True, weights=weights)
+    monkeypatch.setenv("IAN_STREAMK", "1")               # third handle: the pair kernel's stream-K schedule (ordered fix-up)
+    pair_sk = npe.IAN("IAN_simple.py", True, weights=weights)
     rng = np.random.default_rng(41)
     try:
+        x = rng.uniform(-1, 1, (70, 3, 64, 64)).astype(np.float32)
+        xa, za = one.reconstruct(x, return_z=True)
+        xs, zs = pair_sk.reconstruct(x, return_z=True)   # another float32 summation order where a tile is cut: rerun tolerances
+        assert np.abs(za - zs).max() <= Z_RERUN and np.abs(xa - xs).max() <= X_RERUN
+        xs2, zs2 = pair_sk.reconstruct(x, return_z=True)
+        assert np.array_equal(xs, xs2) and np.array_equal(zs, zs2)      # ... and deterministic
         for n in (1, 3, 9, 70):
             x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
             z = rng.standard_normal((n, 100)).astype(np.float32)
@@ -387,3 +395,4 @@ def test_pair_kernel_equals_one_cta_kernel(npe, weights, monkeypatch):
     finally:
         one.close()
         pair.close()
+        pair_sk.close()
