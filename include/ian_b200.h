@@ -23,7 +23,7 @@
  *   - environment, read by ian_create: IAN_CHUNK=<n> images per internal chunk (default 512); IAN_PATH=simt selects
  *     the FFMA verification kernels; IAN_STREAMK=0 disables stream-K scheduling; IAN_GRAPHS=0 disables the CUDA-graph
  *     replay that *_host calls with <= 32 images use; IAN_TC2=0 keeps every layer on the one-CTA tap-GEMM kernel
- *     (default: layers with >= IAN_TC2_MIN (74) whole pair-tiles run on CTA pairs, tcgen05 cta_group::2);
+ *     (default: layers with >= IAN_TC2_MIN (37) whole pair-tiles run on CTA pairs, tcgen05 cta_group::2);
  *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_SPLITK=0 disables split-K (tests); IAN_PUSH_CTAS=<n> sizes the
  *     copy kernel of the pipelined all-gather.
  */

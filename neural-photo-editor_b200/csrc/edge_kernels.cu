@@ -416,7 +416,8 @@ __global__ void head_g_kernel(const float* __restrict__ ha, float* __restrict__ 
 }
 
 __global__ void head_b_out_kernel(const float* __restrict__ ha, const float* __restrict__ rg, const int* __restrict__ taps,
-                                  const float* __restrict__ wbb, int ntaps, float* __restrict__ xhat, int n) {
+                                  const float* __restrict__ wbb, int ntaps, float* __restrict__ xhat,
+                                  float* __restrict__ bsave /*nullable: (n,64,64,2) = B, kept for the brush backward*/, int n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
@@ -433,6 +434,7 @@ __global__ void head_b_out_kernel(const float* __restrict__ ha, const float* __r
   }
   const float4 me = *reinterpret_cast<const float4*>(rg + i * 4);
   const float B0 = sigmoidf_(b0), B1 = sigmoidf_(b1);
+  if (bsave) *reinterpret_cast<float2*>(bsave + i * 2) = make_float2(B0, B1);
   float* o = xhat + img * 3 * 4096 + p * 64 + q;
   o[0] = 2.f * (me.x / (me.x + me.y + 1e-8f)) - 1.f;     // beta_layer (layers.py:408)
   o[4096] = 2.f * (me.z / (me.z + me.w + 1e-8f)) - 1.f;
@@ -573,12 +575,148 @@ int launch_head_gather(const float* tt, int tt_is_bf16, const int* taps, int nta
 }
 
 int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
-                         float* xhat, int n, cudaStream_t st) {
+                         float* xhat, float* bsave, int n, cudaStream_t st) {
   const long long npix = (long long)n * 4096;
   const unsigned blocks = (unsigned)((npix + 255) / 256);
   head_r_kernel<<<blocks, 256, 0, st>>>(ha, rg, npix);
   head_g_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wgb, ntaps, n);
-  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wbb, ntaps, xhat, n);
+  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wbb, ntaps, xhat, bsave, n);
   return cudaGetLastError() == cudaSuccess ? 3 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Brush gradient through the RGB-Beta head (T.grad of API.py:59,64 on the IAN.py / IANv1.py graphs; forward:
+// IAN.py:183-207, layers.py:397-408).  dpre (n,64,64,8) float32 ends up holding d loss / d [preR0 preR1 preG0 preG1 preB0
+// preB1 . .] -- the gradient w.r.t. the three 128->2 MDC convolutions of the feature map -- in three passes that
+// mirror the autoregressive forward in reverse (B, then G, then R):
+//   seed : dL/dx_hat over the brush box (lighten: 1/(3 bh bw); RGB: 2 (x_hat - t)/(3 bh bw)), beta_layer backward
+//          d out/d a = 2 (b + eps)/(a+b+eps)^2, d out/d b = -2 a/(a+b+eps)^2, and dpreB = dB * B (1-B)
+//   g    : d[R,G] += MDC_Bb^T(dpreB)   (33 dilated taps, 2 -> 4 channels);  dpreG = dG * G (1-G)
+//   r    : dR     += MDC_Gb^T(dpreG)   (2 -> 2 channels);                   dpreR = dR * R (1-R)
+// and im2col lays dpre out as the K = 33 taps x 6 operand of the dense backward GEMM (dh = A2 * Wcomp).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_bwd_seed_kernel(const float* __restrict__ xhat, const float* __restrict__ rg,
+                                                            const float* __restrict__ bsave, const int32_t* __restrict__ boxes,
+                                                            const float* __restrict__ target, int target_is_frame,
+                                                            float* __restrict__ dpre, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * 4096) return;
+  const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
+  const int k = (int)(i >> 12);
+  const int c1 = max(boxes[k * 4 + 0], 0), r1 = max(boxes[k * 4 + 1], 0);
+  const int c2 = min(boxes[k * 4 + 2], 64), r2 = min(boxes[k * 4 + 3], 64);
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (p >= r1 && p < r2 && q >= c1 && q < c2) {
+    const float inv = 1.f / (3.f * (float)(r2 - r1) * (float)(c2 - c1));
+    const float4 rgv = *reinterpret_cast<const float4*>(rg + i * 4);
+    const float2 bv = *reinterpret_cast<const float2*>(bsave + i * 2);
+    const float a[3] = {rgv.x, rgv.z, bv.x}, b[3] = {rgv.y, rgv.w, bv.y};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xv = xhat[((long long)(k * 3 + c) * 64 + p) * 64 + q];
+      float sd = inv;
+      if (target) {
+        const float t = target_is_frame ? target[((long long)(k * 3 + c) * 64 + p) * 64 + q] : target[k * 3 + c];
+        sd = 2.f * inv * (xv - t);
+      }
+      const float s = a[c] + b[c] + 1e-8f;
+      o[2 * c] = sd * 2.f * (b[c] + 1e-8f) / (s * s);
+      o[2 * c + 1] = -sd * 2.f * a[c] / (s * s);
+    }
+    o[4] *= bv.x * (1.f - bv.x);                         // dpreB
+    o[5] *= bv.y * (1.f - bv.y);
+  }
+  float4* dp = reinterpret_cast<float4*>(dpre + i * 8);
+  dp[0] = make_float4(o[0], o[1], o[2], o[3]);
+  dp[1] = make_float4(o[4], o[5], 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) head_bwd_g_kernel(float* __restrict__ dpre, const float* __restrict__ rg,
+                                                         const int* __restrict__ taps, const float* __restrict__ wbb, int ntaps, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * 4096) return;
+  const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
+  const long long img = i >> 12;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < ntaps; ++t) {                      // forward read (p + off): the transpose reads (p - off)
+    const int pp = p - taps[2 * t], qq = q - taps[2 * t + 1];
+    if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
+    const float2 g = *reinterpret_cast<const float2*>(dpre + ((img * 64 + pp) * 64 + qq) * 8 + 4);   // dpreB of the reader
+    const float4 w0 = *reinterpret_cast<const float4*>(wbb + t * 8);       // out 0: in 0..3
+    const float4 w1 = *reinterpret_cast<const float4*>(wbb + t * 8 + 4);   // out 1: in 0..3
+    d[0] = fmaf(g.x, w0.x, fmaf(g.y, w1.x, d[0]));
+    d[1] = fmaf(g.x, w0.y, fmaf(g.y, w1.y, d[1]));
+    d[2] = fmaf(g.x, w0.z, fmaf(g.y, w1.z, d[2]));
+    d[3] = fmaf(g.x, w0.w, fmaf(g.y, w1.w, d[3]));
+  }
+  float4 own = *reinterpret_cast<const float4*>(dpre + i * 8);
+  const float4 rgv = *reinterpret_cast<const float4*>(rg + i * 4);
+  own.x += d[0];
+  own.y += d[1];
+  own.z = (own.z + d[2]) * rgv.z * (1.f - rgv.z);        // dpreG
+  own.w = (own.w + d[3]) * rgv.w * (1.f - rgv.w);
+  *reinterpret_cast<float4*>(dpre + i * 8) = own;        // slots 0..3 only: the neighbours read slots 4,5
+}
+
+__global__ void __launch_bounds__(256) head_bwd_r_kernel(float* __restrict__ dpre, const float* __restrict__ rg,
+                                                         const int* __restrict__ taps, const float* __restrict__ wgb, int ntaps, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * 4096) return;
+  const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
+  const long long img = i >> 12;
+  float d0 = 0.f, d1 = 0.f;
+  for (int t = 0; t < ntaps; ++t) {
+    const int pp = p - taps[2 * t], qq = q - taps[2 * t + 1];
+    if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
+    const float2 g = *reinterpret_cast<const float2*>(dpre + ((img * 64 + pp) * 64 + qq) * 8 + 2);   // dpreG of the reader
+    const float4 w = *reinterpret_cast<const float4*>(wgb + t * 4);        // [out0: in0,in1 | out1: in0,in1]
+    d0 = fmaf(g.x, w.x, fmaf(g.y, w.z, d0));
+    d1 = fmaf(g.x, w.y, fmaf(g.y, w.w, d1));
+  }
+  float2 own = *reinterpret_cast<const float2*>(dpre + i * 8);
+  const float2 r = *reinterpret_cast<const float2*>(rg + i * 4);
+  own.x = (own.x + d0) * r.x * (1.f - r.x);              // dpreR
+  own.y = (own.y + d1) * r.y * (1.f - r.y);
+  *reinterpret_cast<float2*>(dpre + i * 8) = own;        // slots 0,1 only: the neighbours read slots 2,3
+}
+
+// A2[pix][t*6 + f] = dpre[pix - off_t][f] as bf16 hi|lo planes (n,64,64,256); columns 198..255 stay zero (allocation memset)
+__global__ void __launch_bounds__(256) head_bwd_im2col_kernel(const float* __restrict__ dpre, const int* __restrict__ taps, int ntaps,
+                                                              __nv_bfloat16* __restrict__ a2, long long plane, int n) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * 4096 * ntaps) return;
+  const int t = (int)(idx % ntaps);
+  const long long pix = idx / ntaps;
+  const int q = (int)(pix & 63), p = (int)((pix >> 6) & 63);
+  const long long img = pix >> 12;
+  const int pp = p - taps[2 * t], qq = q - taps[2 * t + 1];
+  float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pp >= 0 && pp <= 63 && qq >= 0 && qq <= 63) {
+    const float* src = dpre + ((img * 64 + pp) * 64 + qq) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float2 b = *reinterpret_cast<const float2*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
+  }
+  __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(a2 + pix * 256 + t * 6);
+  __nv_bfloat162* ol = reinterpret_cast<__nv_bfloat162*>(a2 + plane + pix * 256 + t * 6);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    const float2 hf = __bfloat1622float2(hi);
+    oh[j] = hi;
+    ol[j] = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+  }
+}
+
+int launch_head_bwd(const float* xhat, const float* rg, const float* bsave, const int32_t* boxes, const float* target,
+                    int target_is_frame, const int* taps, const float* wgb, const float* wbb, int ntaps, float* dpre,
+                    __nv_bfloat16* a2, long long a2_plane, int n, cudaStream_t st) {
+  const long long npix = (long long)n * 4096;
+  const unsigned blocks = (unsigned)((npix + 255) / 256);
+  head_bwd_seed_kernel<<<blocks, 256, 0, st>>>(xhat, rg, bsave, boxes, target, target_is_frame, dpre, n);
+  head_bwd_g_kernel<<<blocks, 256, 0, st>>>(dpre, rg, taps, wbb, ntaps, n);
+  head_bwd_r_kernel<<<blocks, 256, 0, st>>>(dpre, rg, taps, wgb, ntaps, n);
+  head_bwd_im2col_kernel<<<(unsigned)((npix * ntaps + 255) / 256), 256, 0, st>>>(dpre, taps, ntaps, a2, a2_plane, n);
+  return cudaGetLastError() == cudaSuccess ? 4 : -1;
 }
 }  // namespace ian

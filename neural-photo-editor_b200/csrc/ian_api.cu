@@ -131,6 +131,9 @@ enum LayerId {
   L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2,
   // full IAN decoder (reference IAN.py:129-207)
   F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD,
+  // brush gradient through the IAN.py / IANv1.py decoders (T.grad at API.py:59,64 on those graphs)
+  F_BWD_HEAD, F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, F_BWD_CONV2, F_BWD_MD1B, F_BWD_MD1A,
+  F_BWD_CONV1, F_BWD_FC2,
   L_COUNT,
   T_CONV1 = L_COUNT, T_DEC_OUT, T_COUNT   // timing-only slots of the two edge kernels
 };
@@ -138,6 +141,9 @@ const char* kLayerNames[T_COUNT] = {"enc_conv2", "enc_conv3", "enc_conv4", "enc_
                                     "dec_conv2", "dec_conv3", "bwd_dec_conv3", "bwd_dec_conv2", "bwd_dec_conv1", "bwd_l_dec_fc2",
                                     "full_dec_fc2", "full_dec_conv1", "dec_conv2a", "dec_conv2a2", "full_dec_conv2", "dec_conv3a", "dec_conv3a2",
                                     "full_dec_conv3", "dec_conv4a", "dec_conv4a2", "full_dec_conv4", "rgb_head",
+                                    "bwd_rgb_head", "bwd_full_dec_conv4", "bwd_dec_conv4a2", "bwd_dec_conv4a", "bwd_full_dec_conv3",
+                                    "bwd_dec_conv3a2", "bwd_dec_conv3a", "bwd_full_dec_conv2", "bwd_dec_conv2a2", "bwd_dec_conv2a",
+                                    "bwd_full_dec_conv1", "bwd_full_dec_fc2",
                                     "enc_conv1", "dec_out"};
 
 struct DevWeights {           // one GEMM layer's B operand + epilogue vectors
@@ -163,7 +169,7 @@ struct ian_handle {
   bool streamk = true;
   bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
-  int tc2_min_tiles = 74;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN)
+  int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
   bool graphs = true;          // replay small-batch host calls as CUDA graphs (IAN_GRAPHS=0 turns it off)
   bool capturing = false;
@@ -203,6 +209,9 @@ struct ian_handle {
   int* head_taps = nullptr;                 // [33][2] (dy,dx) of the scales-[2,3,4] MDC
   float *head_wgb = nullptr, *head_wbb = nullptr;   // composite G_b [33][2][2], B_b [33][2][4]
   int head_ntaps = 0;
+  __nv_bfloat16* head_tc_wt = nullptr;      // fused head (head_tc.cu): [2 planes][3 convs x 80 rows][128] bf16, row = sorted tap*2 + filter
+  int head_dy_start[10] = {0};              // taps sorted by row offset: taps with dy = -4 + i are [dy_start[i], dy_start[i+1])
+  int head_dx[33] = {0};
   std::map<int, Plan*> plans;
   int max_chunk = 512;
   bool timing = false;
@@ -254,10 +263,14 @@ struct Plan {
   Planes fh0, fx1, ft1, fu1, fy1, fx2, ft2, fu2, fy2, fx3, ft3, fu3, fy3, fh4;
   uint8_t* stroke = nullptr;     // ian_paint_stroke_host staging (allocated on first use)
   float *z0 = nullptr, *ha = nullptr, *rg = nullptr, *tt = nullptr;   // tt: head tap table [n][198][4096]
+  // brush backward of the flow models: saved B, head gradient, its im2col operand, and the per-stage gradients
+  float *bsave = nullptr, *dpre = nullptr;
+  Planes dha2, d4, ds3, du3, dx3, ds2, du2, dx2, ds1, du1, dx1, dfh0;
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
   Tc2Maps* maps2[L_COUNT] = {nullptr};   // CTA-pair kernel (only for layers with enough whole tiles; see build_pair_maps)
   DecOutMaps* decout_maps = nullptr;
+  HeadMaps* head_maps = nullptr;
   // pipelined host API: double-buffered boundary tensors + events (allocated on first use)
   float *sx[2] = {nullptr, nullptr}, *sz[2] = {nullptr, nullptr}, *sxh[2] = {nullptr, nullptr};
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -356,6 +369,15 @@ void taps_mdc(TapGemm& g, const std::vector<int>& scales) {
   g.nphase = 1;
   g.phase[0] = {0, (int)off.size(), 0, 0};
   for (size_t t = 0; t < off.size(); ++t) g.taps[t] = {0, (int16_t)off[t].first, (int16_t)off[t].second, (int16_t)t};
+  g.sh = g.sw = 1;
+  g.osh = g.osw = 1;
+}
+
+void taps_mdc_bwd(TapGemm& g, const std::vector<int>& scales) {   // din[q] = sum_t dout[q - off_t] * comp_t^T
+  const auto off = mdc_offsets(scales);
+  g.nphase = 1;
+  g.phase[0] = {0, (int)off.size(), 0, 0};
+  for (size_t t = 0; t < off.size(); ++t) g.taps[t] = {0, (int16_t)(-off[t].first), (int16_t)(-off[t].second), (int16_t)t};
   g.sh = g.sw = 1;
   g.osh = g.osw = 1;
 }
@@ -463,11 +485,29 @@ int build_plan_v1(ian_handle* h, Plan* pl, Plan** out) {
   g[F_DEC_CONV4].act = ACT_RELU; outp(g[F_DEC_CONV4], pl->fh4);
   set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
   g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
+  // ---- brush backward (T.grad of API.py:59,64 on this graph): head GEMM, then the four deconvs' backward-data and the dense
+  auto bwd = [&](int l, const Planes& in, int Hin, int Cin, const Planes& out, const Planes* mask, int act) {
+    set_io(g[l], in, n, Hin, Hin, Cin, Hin / 2, Hin / 2, h->w[l], Hin / 2, Hin / 2); taps_deconv_bwd(g[l]);
+    g[l].act = act; g[l].mask = mask ? mask->p : nullptr; g[l].mask_slope = 0.f; outp(g[l], out);
+  };
+  set_io(g[F_BWD_HEAD], pl->dha2, n, 64, 64, 256, 64, 64, h->w[F_BWD_HEAD], 64, 64); taps_dense(g[F_BWD_HEAD]);
+  g[F_BWD_HEAD].act = ACT_MASK; g[F_BWD_HEAD].mask = pl->fh4.p; outp(g[F_BWD_HEAD], pl->d4);
+  bwd(F_BWD_CONV4, pl->d4, 64, 128, pl->d3, &pl->h3, ACT_MASK);
+  bwd(L_BWD_CONV3, pl->d3, 32, 128, pl->d2, &pl->h2, ACT_MASK);
+  bwd(L_BWD_CONV2, pl->d2, 16, 256, pl->d1, &pl->h1, ACT_MASK);
+  bwd(L_BWD_CONV1, pl->d1, 8, 512, pl->d0, nullptr, ACT_NONE);          // l_dec_fc2 is linear here (IANv1.py:125-130)
+  set_io(g[L_BWD_FC2], pl->d0, n, 1, 1, 16384, 1, 1, h->w[L_BWD_FC2], 1, 1); taps_dense(g[L_BWD_FC2]);
+  g[L_BWD_FC2].act = ACT_NONE; g[L_BWD_FC2].out_f32 = pl->gpad; g[L_BWD_FC2].ksplit = 0;
   mark_splitk_candidates(pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1,
-                              L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4});
+                              L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4, F_BWD_HEAD, F_BWD_CONV4, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1});
   int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2,
-                           L_DEC_CONV3, F_DEC_CONV4, F_HEAD});
+                           L_DEC_CONV3, F_DEC_CONV4, F_HEAD, F_BWD_HEAD, F_BWD_CONV4, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2});
   if (rc != IAN_OK) return rc;
+  {
+    char err[256] = {0};
+    pl->head_maps = head_build_maps(pl->fh4.p, pl->fh4.plane, n, h->head_tc_wt, 3 * 80 * 128, err, sizeof(err));
+    if (!pl->head_maps) return fail(h, IAN_ERR_CUDA, "rgb head: %s", err);
+  }
   *out = pl;
   return IAN_OK;
 }
@@ -502,11 +542,44 @@ int build_plan_full(ian_handle* h, Plan* pl, Plan** out) {
   // times), written channel-major; the dilated taps are applied afterwards as coalesced shifted reads (head_gather)
   set_io(g[F_HEAD], pl->fh4, n, 64, 64, 128, 64, 64, h->w[F_HEAD], 64, 64); taps_dense(g[F_HEAD]);
   g[F_HEAD].act = ACT_NONE; g[F_HEAD].out_f32_t = pl->tt; g[F_HEAD].cout_real = 198;
+  // ---- brush backward (T.grad of API.py:59,64 on this graph).  LeakyRectify(0.2) backward = mask slope 0.2 on the sign of
+  // the stored forward activation; MDBLOCK (layers.py:411-416) y = lrelu(BN2(x + M2(u))), u = lrelu(BN1(M1(t))), t = lrelu(BN0(x)):
+  //   ds = dy * lrelu'(y) * s2 ;  du = M2^T(ds) * lrelu'(u) * s1 ;  dx = M1^T(du) * lrelu'(t) * s0 + ds
+  set_io(g[F_BWD_HEAD], pl->dha2, n, 64, 64, 256, 64, 64, h->w[F_BWD_HEAD], 64, 64); taps_dense(g[F_BWD_HEAD]);
+  g[F_BWD_HEAD].act = ACT_MASK; g[F_BWD_HEAD].mask = pl->fh4.p; g[F_BWD_HEAD].mask_slope = 0.2f; outp(g[F_BWD_HEAD], pl->d4);
+  struct BStage { int dconv, mdb, mda; const Planes *din, *ds, *du, *dx, *y, *u, *t; int Hin, Cin, Cout; std::vector<int> scales; };
+  // dconv: backward-data of the deconv ABOVE the block (its input gradient `din` lives at 2x the block's resolution)
+  const BStage bs[3] = {{F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, &pl->d4, &pl->ds3, &pl->du3, &pl->dx3, &pl->fy3, &pl->fu3, &pl->ft3, 64, 128, 128, {0, 2, 3}},
+                        {F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, &pl->dx3, &pl->ds2, &pl->du2, &pl->dx2, &pl->fy2, &pl->fu2, &pl->ft2, 32, 128, 256, {0, 2, 3}},
+                        {F_BWD_CONV2, F_BWD_MD1B, F_BWD_MD1A, &pl->dx2, &pl->ds1, &pl->du1, &pl->dx1, &pl->fy1, &pl->fu1, &pl->ft1, 16, 256, 512, {0, 2}}};
+  for (const BStage& b : bs) {
+    const int Ho = b.Hin / 2;
+    set_io(g[b.dconv], *b.din, n, b.Hin, b.Hin, b.Cin, Ho, Ho, h->w[b.dconv], Ho, Ho); taps_deconv_bwd(g[b.dconv]);
+    g[b.dconv].act = ACT_MASK; g[b.dconv].mask = b.y->p; g[b.dconv].mask_slope = 0.2f; outp(g[b.dconv], *b.ds);
+    set_io(g[b.mdb], *b.ds, n, Ho, Ho, b.Cout, Ho, Ho, h->w[b.mdb], Ho, Ho); taps_mdc_bwd(g[b.mdb], b.scales);
+    g[b.mdb].act = ACT_MASK; g[b.mdb].mask = b.u->p; g[b.mdb].mask_slope = 0.2f; outp(g[b.mdb], *b.du);
+    set_io(g[b.mda], *b.du, n, Ho, Ho, b.Cout, Ho, Ho, h->w[b.mda], Ho, Ho); taps_mdc_bwd(g[b.mda], b.scales);
+    g[b.mda].act = ACT_MASK; g[b.mda].mask = b.t->p; g[b.mda].mask_slope = 0.2f; outp(g[b.mda], *b.dx);
+    g[b.mda].res = b.ds->p; g[b.mda].res_plane = b.ds->plane; g[b.mda].res_after = 1;
+  }
+  set_io(g[F_BWD_CONV1], pl->dx1, n, 8, 8, 512, 4, 4, h->w[F_BWD_CONV1], 4, 4); taps_deconv_bwd(g[F_BWD_CONV1]);
+  g[F_BWD_CONV1].act = ACT_MASK; g[F_BWD_CONV1].mask = pl->fh0.p; g[F_BWD_CONV1].mask_slope = 0.2f; outp(g[F_BWD_CONV1], pl->dfh0);
+  set_io(g[F_BWD_FC2], pl->dfh0, n, 1, 1, 8192, 1, 1, h->w[F_BWD_FC2], 1, 1); taps_dense(g[F_BWD_FC2]);
+  g[F_BWD_FC2].act = ACT_NONE; g[F_BWD_FC2].out_f32 = pl->gpad; g[F_BWD_FC2].ksplit = 0;
   mark_splitk_candidates(pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A,
-                              F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4});
+                              F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4,
+                              F_BWD_HEAD, F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, F_BWD_CONV2,
+                              F_BWD_MD1B, F_BWD_MD1A, F_BWD_CONV1});
   int rc = finish_maps(h, pl, {L_ENC_CONV2, L_ENC_CONV3, L_ENC_CONV4, L_ENC_FC1, L_ENC_HEAD, F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B,
-                               F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD});
+                               F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD,
+                               F_BWD_HEAD, F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, F_BWD_CONV2,
+                               F_BWD_MD1B, F_BWD_MD1A, F_BWD_CONV1, F_BWD_FC2});
   if (rc != IAN_OK) return rc;
+  {
+    char err[256] = {0};
+    pl->head_maps = head_build_maps(pl->fh4.p, pl->fh4.plane, n, h->head_tc_wt, 3 * 80 * 128, err, sizeof(err));
+    if (!pl->head_maps) return fail(h, IAN_ERR_CUDA, "rgb head: %s", err);
+  }
   *out = pl;
   return IAN_OK;
 }
@@ -528,6 +601,9 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   if (v1) {
     AP(fh4, N * 4096 * 128)
     AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4) AB(tt, N * 198 * 4096)
+    AB(bsave, N * 4096 * 2) AB(dpre, N * 4096 * 8) AP(dha2, N * 4096 * 256) AP(d4, N * 4096 * 128)
+    AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
+    AB(gpad, N * 128) AB(target, N * 3 * 4096) AB(boxes, N * 4)
   } else if (!full) {
     AP(d3, N * 32 * 32 * 128) AP(d2, N * 16 * 16 * 256) AP(d1, N * 8 * 8 * 512) AP(d0, N * 16384)
     AB(gpad, N * 128) AB(target, N * 3 * 4096) AB(boxes, N * 4)
@@ -538,6 +614,12 @@ int build_plan(ian_handle* h, int n, Plan** out) {
     AP(fx3, N * 1024 * 128) AP(ft3, N * 1024 * 128) AP(fu3, N * 1024 * 128) AP(fy3, N * 1024 * 128)
     AP(fh4, N * 4096 * 128)
     AB(z0, N * 100) AB(ha, N * 4096 * 16) AB(rg, N * 4096 * 4) AB(tt, N * 198 * 4096)
+    AB(bsave, N * 4096 * 2) AB(dpre, N * 4096 * 8) AP(dha2, N * 4096 * 256) AP(d4, N * 4096 * 128)
+    AP(ds3, N * 1024 * 128) AP(du3, N * 1024 * 128) AP(dx3, N * 1024 * 128)
+    AP(ds2, N * 256 * 256) AP(du2, N * 256 * 256) AP(dx2, N * 256 * 256)
+    AP(ds1, N * 64 * 512) AP(du1, N * 64 * 512) AP(dx1, N * 64 * 512)
+    AP(dfh0, N * 8192)
+    AB(gpad, N * 128) AB(target, N * 3 * 4096) AB(boxes, N * 4)
   }
 #undef AP
 #undef AB
@@ -607,6 +689,7 @@ void free_plan(Plan* pl) {
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps[l]) tc_free_maps(pl->maps[l]);
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps2[l]) tc2_free_maps(pl->maps2[l]);
   if (pl->decout_maps) decout_free_maps(pl->decout_maps);
+  if (pl->head_maps) head_free_maps(pl->head_maps);
   for (auto& gs : pl->graph) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   delete pl;
 }
@@ -691,22 +774,37 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
   return IAN_OK;
 }
 
+// RGB-Beta head (IAN.py:183-207) from the feature map fh4.  Tensor-core path: head_tc.cu (dense GEMM + on-chip tap gather,
+// then the autoregressive part in one kernel).  Verification path: the dense GEMM into the HBM tap table + gather + the
+// three per-pixel kernels of round 1 -- a second, independent formulation.
+int run_head(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
+  if (h->path == IAN_PATH_TC) {
+    {
+      ScopedTimer tm(h, F_HEAD, st);
+      LAUNCH_TRY(h, launch_head_tc(pl->head_maps, h->head_dy_start, h->head_dx, h->passes, pl->ha, pl->n, st));
+    }
+    LAUNCH_TRY(h, launch_head_rgb(pl->ha, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->rg, pl->bsave, pl->n, st));
+    return IAN_OK;
+  }
+  int rc;
+  if ((rc = run_gemm(h, pl, F_HEAD, st)) != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
+  LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->bsave, pl->n, st));
+  return IAN_OK;
+}
+
 // zp must already hold the latent planes
 int run_decode_from_planes(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
   int rc;
   if (h->model_kind == IAN_MODEL_V1) {
-    for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4, F_HEAD})
+    for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3, F_DEC_CONV4})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
-    LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
-    return IAN_OK;
+    return run_head(h, pl, xhat, st);
   }
   if (h->model_kind == IAN_MODEL_FULL) {
-    for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4, F_HEAD})
+    for (int l : {F_DEC_FC2, F_DEC_CONV1, F_MD1A, F_MD1B, F_DEC_CONV2, F_MD2A, F_MD2B, F_DEC_CONV3, F_MD3A, F_MD3B, F_DEC_CONV4})
       if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
-    LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
-    LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->n, st));
-    return IAN_OK;
+    return run_head(h, pl, xhat, st);
   }
   for (int l : {L_DEC_FC2, L_DEC_CONV1, L_DEC_CONV2, L_DEC_CONV3})
     if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
@@ -730,6 +828,20 @@ int run_grad_core(ian_handle* h, Plan* pl, const int32_t* boxes, const float* ta
                   cudaStream_t st) {
   int rc;
   if ((rc = run_decode_from_planes(h, pl, pl->xhat, st)) != IAN_OK) return rc;
+  if (has_flow(h)) {
+    // the gradient is w.r.t. l_Z, the decoder's input (API.py:46: X_hat = get_output(l_out, {l_Z: Z})): no MADE/IAF backward
+    LAUNCH_TRY(h, launch_head_bwd(pl->xhat, pl->rg, pl->bsave, boxes, target, target_is_frame, h->head_taps, h->head_wgb,
+                                  h->head_wbb, h->head_ntaps, pl->dpre, pl->dha2.p, pl->dha2.plane, pl->n, st));
+    if (h->model_kind == IAN_MODEL_V1) {
+      for (int l : {F_BWD_HEAD, F_BWD_CONV4, L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2})
+        if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+    } else {
+      for (int l : {F_BWD_HEAD, F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, F_BWD_CONV2,
+                    F_BWD_MD1B, F_BWD_MD1A, F_BWD_CONV1, F_BWD_FC2})
+        if ((rc = run_gemm(h, pl, l, st)) != IAN_OK) return rc;
+    }
+    return IAN_OK;
+  }
   LAUNCH_TRY(h, launch_brush_seed_bwd(pl->xhat, boxes, target, target_is_frame, h->decout_wt, h->w[L_DEC_CONV3].scale,
                                       pl->h3.p, pl->d3.p, pl->d3.plane, pl->n, st));
   for (int l : {L_BWD_CONV3, L_BWD_CONV2, L_BWD_CONV1, L_BWD_FC2})
@@ -737,11 +849,7 @@ int run_grad_core(ian_handle* h, Plan* pl, const int32_t* boxes, const float* ta
   return IAN_OK;
 }
 
-int check_brush_supported(ian_handle* h) {
-  if (h && h->model_kind != IAN_MODEL_SIMPLE)
-    return fail(h, IAN_ERR_UNSUPPORTED, "brush gradients are implemented for the IAN_simple graph only (what NPE.py loads)");
-  return IAN_OK;
-}
+int check_brush_supported(ian_handle*) { return IAN_OK; }   // all three graphs have their decoder backward
 
 int check_ready(ian_handle* h, int n, const void* a, const void* b) {
   if (!h) return IAN_ERR_INVALID;
@@ -881,6 +989,22 @@ void deconv_fwd_tiles(const std::vector<float>& W, int Cin, int Cout, std::vecto
   for (int ci = 0; ci < Cin; ++ci)
     for (int co = 0; co < Cout; ++co)
       for (int t = 0; t < 25; ++t) B[((size_t)t * Cout + co) * Cin + ci] = W[((size_t)ci * Cout + co) * 25 + t];
+}
+
+// backward-data of the same layer: the gradient w.r.t. the deconv's INPUT is a stride-2 convolution of the output gradient
+// with tiles B[k][ci][co] = W[ci][co][k] (GEMM Cout = the deconv's Cin, GEMM Cin = the deconv's Cout, padded to CoutPad)
+void deconv_bwd_tiles(const std::vector<float>& W, int Cin, int Cout, int CoutPad, std::vector<float>& B) {
+  B.assign((size_t)25 * Cin * CoutPad, 0.f);
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int co = 0; co < Cout; ++co)
+      for (int t = 0; t < 25; ++t) B[((size_t)t * Cin + ci) * CoutPad + co] = W[((size_t)ci * Cout + co) * 25 + t];
+}
+// transposed composite MDC tiles: comp [nt][F][C] -> [nt][C][F]
+void transpose_tiles(const std::vector<float>& comp, int nt, int F, int C, std::vector<float>& out) {
+  out.assign((size_t)nt * C * F, 0.f);
+  for (int t = 0; t < nt; ++t)
+    for (int f = 0; f < F; ++f)
+      for (int c = 0; c < C; ++c) out[((size_t)t * C + c) * F + f] = comp[((size_t)t * F + f) * C + c];
 }
 
 int prepare_simple_decoder(ian_handle* h) {
@@ -1033,7 +1157,7 @@ int prepare_made(ian_handle* h) {
 }
 
 // RGB-Beta head weights for a feature map with C real channels (128 for IAN.py, 64 for IANv1.py) stored 128 wide
-int prepare_head(ian_handle* h, int C) {
+int prepare_head(ian_handle* h, int C, const std::vector<float>& scale_below /*BN scale of the feature map (128 wide)*/) {
   int rc;
   std::vector<float> B, sc, comp;
   // ---- RGB-Beta head (IAN.py:183-207): the three 128->2 MDC convs as one 16-row tile [R | G_a | B_a | 0...]
@@ -1053,11 +1177,42 @@ int prepare_head(ian_handle* h, int C) {
     }
     sc.assign(256, 1.f);
     if ((rc = upload_gemm_weights(h, F_HEAD, B, 1, 256, 128, sc, {})) != IAN_OK) return rc;
+    // backward: dh[c] = sum_k A2[k] * B[k][c], k = t*6 + (2 conv + filter): the transposed tile, GEMM Cout = 128, Cin = 256
+    std::vector<float> Bt((size_t)128 * 256, 0.f);
+    for (int k = 0; k < 256; ++k)
+      for (int c = 0; c < 128; ++c) Bt[(size_t)c * 256 + k] = B[(size_t)k * 128 + c];
+    if ((rc = upload_gemm_weights(h, F_BWD_HEAD, Bt, 1, 128, 256, scale_below, {})) != IAN_OK) return rc;
     std::vector<int> taps(nt * 2);
     for (int t = 0; t < nt; ++t) { taps[2 * t] = off[t].first; taps[2 * t + 1] = off[t].second; }
     CUDA_TRY(h, cudaMalloc((void**)&h->head_taps, taps.size() * 4));
     CUDA_TRY(h, cudaMemcpy(h->head_taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
     h->head_ntaps = nt;
+    // fused head (head_tc.cu): taps sorted by row offset (stable), per conv k one 80-row tile: row = sorted tap * 2 + filter
+    {
+      std::vector<int> order;
+      int pos = 0;
+      for (int dy = -4; dy <= 4; ++dy) {
+        h->head_dy_start[dy + 4] = pos;
+        for (int t = 0; t < nt; ++t)
+          if (off[t].first == dy) { order.push_back(t); h->head_dx[pos++] = off[t].second; }
+      }
+      h->head_dy_start[9] = pos;
+      if (pos != 33) return fail(h, IAN_ERR_STATE, "head taps do not fit the [-4,4] row-offset window");
+      std::vector<uint16_t> planes((size_t)2 * 3 * 80 * 128, 0);
+      const size_t plane = (size_t)3 * 80 * 128;
+      for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 33; ++j)
+          for (int f = 0; f < 2; ++f)
+            for (int c = 0; c < 128; ++c) {
+              const float w = B[((size_t)(order[j] * 6 + 2 * k + f)) * 128 + c];
+              const uint16_t hi = f2bf(w);
+              const size_t row = (size_t)k * 80 + j * 2 + f;
+              planes[row * 128 + c] = hi;
+              planes[plane + row * 128 + c] = f2bf(w - bf2f(hi));
+            }
+      CUDA_TRY(h, cudaMalloc((void**)&h->head_tc_wt, planes.size() * 2));
+      CUDA_TRY(h, cudaMemcpy(h->head_tc_wt, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
+    }
     mdc_composite(h, "G_b", 2, 2, hs, comp);             // [nt][2 out][2 in]
     CUDA_TRY(h, cudaMalloc((void**)&h->head_wgb, comp.size() * 4));
     CUDA_TRY(h, cudaMemcpy(h->head_wgb, comp.data(), comp.size() * 4, cudaMemcpyHostToDevice));
@@ -1106,7 +1261,28 @@ int prepare_v1_decoder(ian_handle* h) {
     sf.resize(128, 0.f);
     if ((rc = upload_gemm_weights(h, F_DEC_CONV4, B, 25, 128, 128, sc, sf)) != IAN_OK) return rc;
   }
-  return prepare_head(h, 64);
+  // ---- brush backward: each backward GEMM's epilogue applies the BN scale (and the ReLU mask) of the layer BELOW it
+  std::vector<float> s4 = sc, s3, s2, s1, f_;              // s4: bnorm_dc4 scale (64 real channels, padded with zeros)
+  fold_bn(h, "bnorm_dc3", 128, s3, f_); fold_bn(h, "bnorm_dc2", 256, s2, f_); fold_bn(h, "bnorm_dc1", 512, s1, f_);
+  deconv_bwd_tiles(P(h, "dec_conv4.W").data, 128, 64, 128, B);
+  if ((rc = upload_gemm_weights(h, F_BWD_CONV4, B, 25, 128, 128, s3, {})) != IAN_OK) return rc;
+  deconv_bwd_tiles(P(h, "dec_conv3.W").data, 256, 128, 128, B);
+  if ((rc = upload_gemm_weights(h, L_BWD_CONV3, B, 25, 256, 128, s2, {})) != IAN_OK) return rc;
+  deconv_bwd_tiles(P(h, "dec_conv2.W").data, 512, 256, 256, B);
+  if ((rc = upload_gemm_weights(h, L_BWD_CONV2, B, 25, 512, 256, s1, {})) != IAN_OK) return rc;
+  deconv_bwd_tiles(P(h, "dec_conv1.W").data, 1024, 512, 512, B);
+  if ((rc = upload_gemm_weights(h, L_BWD_CONV1, B, 25, 1024, 512, std::vector<float>(1024, 1.f), {})) != IAN_OK) return rc;
+  {   // dz[k] = sum_col d0[col] * W[k][col]
+    const auto& W = P(h, "l_dec_fc2.W").data;
+    B.assign((size_t)128 * 16384, 0.f);
+    for (int c = 0; c < 1024; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 1024 + c;
+        for (int k = 0; k < 100; ++k) B[(size_t)k * 16384 + col] = W[(size_t)k * 16384 + j];
+      }
+    if ((rc = upload_gemm_weights(h, L_BWD_FC2, B, 1, 128, 16384, std::vector<float>(128, 1.f), {})) != IAN_OK) return rc;
+  }
+  return prepare_head(h, 64, s4);
 }
 
 int prepare_full_decoder(ian_handle* h) {
@@ -1148,7 +1324,40 @@ int prepare_full_decoder(ian_handle* h) {
   deconv_fwd_tiles(P(h, "dec_conv4.W").data, 128, 128, B);
   fold_bn(h, "bnorm_dc4", 128, sc, sf);
   if ((rc = upload_gemm_weights(h, F_DEC_CONV4, B, 25, 128, 128, sc, sf)) != IAN_OK) return rc;
-  if ((rc = prepare_head(h, 128)) != IAN_OK) return rc;
+  if ((rc = prepare_head(h, 128, sc)) != IAN_OK) return rc;
+  // ---- brush backward (see build_plan_full): every backward GEMM's epilogue applies the BN scale of the activation it lands on
+  struct Bk { int dconv, mdb, mda; const char* w_above; int Cin_above, Cout_above; const char* blk; int C; std::vector<int> scales; };
+  // dconv = backward-data of the deconv ABOVE block `blk` (w_above: (Cin_above = this block's C, Cout_above))
+  const Bk bks[3] = {{F_BWD_CONV4, F_BWD_MD3B, F_BWD_MD3A, "dec_conv4.W", 128, 128, "dec_conv4a", 128, {0, 2, 3}},
+                     {F_BWD_CONV3, F_BWD_MD2B, F_BWD_MD2A, "dec_conv3.W", 256, 128, "dec_conv3a", 256, {0, 2, 3}},
+                     {F_BWD_CONV2, F_BWD_MD1B, F_BWD_MD1A, "dec_conv2.W", 512, 256, "dec_conv2a", 512, {0, 2}}};
+  std::vector<float> s0, s1, s2, f_, Bt;
+  for (const Bk& b : bks) {
+    fold_bn(h, std::string(b.blk) + "bnorm0", b.C, s0, f_);
+    fold_bn(h, std::string(b.blk) + "bnorm1", b.C, s1, f_);
+    fold_bn(h, std::string(b.blk) + "bnorm2", b.C, s2, f_);
+    deconv_bwd_tiles(P(h, b.w_above).data, b.Cin_above, b.Cout_above, b.Cout_above, B);
+    if ((rc = upload_gemm_weights(h, b.dconv, B, 25, b.Cin_above, b.Cout_above, s2, {})) != IAN_OK) return rc;
+    const int nt = (int)mdc_offsets(b.scales).size();
+    mdc_composite(h, std::string(b.blk) + "2", b.C, b.C, b.scales, comp);
+    transpose_tiles(comp, nt, b.C, b.C, Bt);
+    if ((rc = upload_gemm_weights(h, b.mdb, Bt, nt, b.C, b.C, s1, {})) != IAN_OK) return rc;
+    mdc_composite(h, b.blk, b.C, b.C, b.scales, comp);
+    transpose_tiles(comp, nt, b.C, b.C, Bt);
+    if ((rc = upload_gemm_weights(h, b.mda, Bt, nt, b.C, b.C, s0, {})) != IAN_OK) return rc;
+  }
+  deconv_bwd_tiles(P(h, "dec_conv1.W").data, 512, 512, 512, B);
+  if ((rc = upload_gemm_weights(h, F_BWD_CONV1, B, 25, 512, 512, std::vector<float>(512, 1.f), {})) != IAN_OK) return rc;
+  {   // dz[k] = sum_col dfh0[col] * W[k][col], col = hw*512 + c
+    const auto& W = P(h, "l_dec_fc2.W").data;
+    B.assign((size_t)128 * 8192, 0.f);
+    for (int c = 0; c < 512; ++c)
+      for (int hw = 0; hw < 16; ++hw) {
+        const int j = c * 16 + hw, col = hw * 512 + c;
+        for (int k = 0; k < 100; ++k) B[(size_t)k * 8192 + col] = W[(size_t)k * 8192 + j];
+      }
+    if ((rc = upload_gemm_weights(h, F_BWD_FC2, B, 1, 128, 8192, std::vector<float>(128, 1.f), {})) != IAN_OK) return rc;
+  }
   return IAN_OK;
 }
 
@@ -1359,6 +1568,7 @@ int ian_destroy(ian_handle* h) {
   cudaFree(h->sk_ws); cudaFree(h->sk_flags);
   cudaFree(h->conv1_tc_wt); if (h->conv1_maps) conv1_free_maps(h->conv1_maps);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
+  cudaFree(h->head_tc_wt);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   if (h->push_stream) { cudaStreamSynchronize(h->push_stream); cudaStreamDestroy(h->push_stream); }
   for (int b = 0; b < 2; ++b) { if (h->g_comp[b]) cudaEventDestroy(h->g_comp[b]); if (h->g_done[b]) cudaEventDestroy(h->g_done[b]); }

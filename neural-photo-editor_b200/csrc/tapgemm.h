@@ -74,7 +74,11 @@ struct TapGemm {
   const float* shift;
   int scale_pix_stride;         // si = co + (oh*Wout+ow)*scale_pix_stride
   int act;
-  const __nv_bfloat16* mask;    // hi plane with the output's geometry (ACT_MASK)
+  const __nv_bfloat16* mask;    // hi plane with the output's geometry (ACT_MASK): v = acc*scale * (mask > 0 ? 1 : mask_slope)
+  float mask_slope;             // 0: rectify backward; 0.2: LeakyRectify(0.2) backward (the mask is the forward ACTIVATION,
+                                // whose sign is the pre-activation's)
+  int res_after;                // 1: `res` is added AFTER the mask/scale (gradient joining a residual branch) instead of before
+                                // BatchNorm (MDBLOCK forward)
   // output: NHWC split planes and/or fp32, pixel = (n*Hout + p*osh+oh0)*Wout + q*osw+ow0
   __nv_bfloat16* out;
   long long out_plane;

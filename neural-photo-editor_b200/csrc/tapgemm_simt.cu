@@ -33,10 +33,12 @@ __device__ __forceinline__ void epilogue_store(const TapGemm& g, float acc, long
     g.out_raw[pix * g.Cout + co] = rh;
     if (g.passes != 1) g.out_raw[g.out_raw_plane + pix * g.Cout + co] = rl;
   }
-  if (g.res) acc += __bfloat162float(g.res[pix * g.Cout + co]) + (g.passes != 1 ? __bfloat162float(g.res[g.res_plane + pix * g.Cout + co]) : 0.f);
+  const float resv = g.res ? __bfloat162float(g.res[pix * g.Cout + co]) + (g.passes != 1 ? __bfloat162float(g.res[g.res_plane + pix * g.Cout + co]) : 0.f) : 0.f;
+  if (!g.res_after) acc += resv;
   if (g.act == ACT_MASK) {
     float mk = __bfloat162float(g.mask[pix * g.Cout + co]);
-    v = mk > 0.f ? acc * sc : 0.f;
+    v = mk > 0.f ? acc * sc : acc * sc * g.mask_slope;
+    if (g.res_after) v += resv;
   } else {
     float sf = g.shift ? g.shift[si] : 0.f;
     v = act_apply(fmaf(acc, sc, sf), g.act);

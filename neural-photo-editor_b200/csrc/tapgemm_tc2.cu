@@ -422,7 +422,7 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
         if (!valid) continue;
         const long long off = pix * g.Cout + co;
         if (g.out_raw) store_split2<CH, PASSES>(g.out_raw + off, g.out_raw_plane, v);   // pre-BN value (MDBLOCK residual input)
-        if (g.res) {                                     // residual add before BatchNorm (MDBLOCK, layers.py:411-416)
+        if (g.res && !g.res_after) {                                     // residual add before BatchNorm (MDBLOCK, layers.py:411-416)
           const uint4* rh = reinterpret_cast<const uint4*>(g.res + off);
           const uint4* rl = reinterpret_cast<const uint4*>(g.res + g.res_plane + off);
 #pragma unroll
@@ -450,7 +450,25 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float sc = g.scale_pix_stride ? __ldg(g.scale + si + j8 * 8 + j) : my_stage[cc + j8 * 8 + j];
-              v[j8 * 8 + j] = __bfloat162float(mb[j]) > 0.f ? v[j8 * 8 + j] * sc : 0.f;
+              v[j8 * 8 + j] = v[j8 * 8 + j] * sc * (__bfloat162float(mb[j]) > 0.f ? 1.f : g.mask_slope);
+            }
+          }
+          if (g.res && g.res_after) {                    // gradient of the block's residual branch joins after the mask/scale
+            const uint4* rh = reinterpret_cast<const uint4*>(g.res + off);
+            const uint4* rl = reinterpret_cast<const uint4*>(g.res + g.res_plane + off);
+#pragma unroll
+            for (int j8 = 0; j8 < CH / 8; ++j8) {
+              const uint4 h4 = __ldg(rh + j8);
+              const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h4);
+              if (PASSES == 3) {
+                const uint4 l4 = __ldg(rl + j8);
+                const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l4);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]) + __bfloat162float(lb[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += __bfloat162float(hb[j]);
+              }
             }
           }
         } else {
@@ -603,6 +621,12 @@ static bool want_streamk_uncached(const TapGemm& g, const Tc2Maps* maps, int bn)
   const int tiles = (int)pair_tiles_bn(g, maps, bn);
   const int G = tc_num_sms() / 2;
   if (tiles < G / 2) return false;
+  // batches that the host API replays as CUDA graphs (<= 32 images; stream-K's epoch is a kernel argument, so captured
+  // launches run whole tiles) keep ONE schedule in both forms; and a tile needs a K loop worth cutting (the dense layers
+  // have 2-16 K steps: a partial-sum round trip costs more than it balances)
+  if (g.n_img <= 32) return false;
+  for (int p = 0; p < g.nphase; ++p)
+    if (g.phase[p].ntaps * (g.Cin / BK) < 24) return false;
   const int per_phase = tiles / g.nphase;
   long long T = 0, makespan = 0;
   std::vector<long long> load(G, 0);
