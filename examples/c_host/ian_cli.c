@@ -75,7 +75,8 @@ static int symbols(void) {
       (anyfn)ian_edit_loop_dev, (anyfn)ian_edit_loop_host, (anyfn)ian_paint_stroke_host,
       (anyfn)ian_set_layer_timing, (anyfn)ian_layer_time_ms, (anyfn)ian_model_param_count,
       (anyfn)ian_model_param_spec, (anyfn)ian_made_mask, (anyfn)ian_debug_made_weights,
-      (anyfn)ian_reconstruct_gather_async_dev, (anyfn)ian_gather_wait_dev};
+      (anyfn)ian_reconstruct_gather_async_dev, (anyfn)ian_gather_wait_dev, (anyfn)ian_bn_batch_stats_dev,
+      (anyfn)ian_bn_train_normalize_dev, (anyfn)ian_minibatch_discrim_dev};
   size_t i, n = sizeof(fn) / sizeof(fn[0]);
   for (i = 0; i < n; ++i)
     if (!fn[i]) return 1;

@@ -209,6 +209,27 @@ int ian_edit_loop_host(ian_handle* h, float* z, const int32_t* boxes, const floa
 int ian_paint_stroke_host(ian_handle* h, float* z, const int32_t* box, const float* rgb_frame, float weight,
                           const uint8_t* recon_u8, const float* error, uint8_t* im_u8, uint8_t* display_u8);
 
+/* ---- training-mode pieces (no trainer here: train_IAN*.py stay the reference's; these are the two forward ops whose
+ * training form differs from the deterministic graphs everything above runs).  Device pointers, float32.
+ *
+ * BatchNorm with BATCH statistics = lasagne BatchNormLayer.get_output_for(deterministic=False), i.e. every BN(...) of
+ * reference IAN_simple.py:84-170 / layers.py:411-416 in training.  x is (n, c, hw) (NCHW with hw = H*W; dense layers: hw = 1).
+ *   ian_bn_batch_stats_dev      per-channel sum and sum of squares (float64 [c] each) over (n, hw): warp-shuffle reductions,
+ *                               fixed order, bit-reproducible.  Data-parallel ranks all-reduce the two arrays here
+ *                               (cross-GPU synchronised BN) and pass the GLOBAL element count to the second call.
+ *   ian_bn_train_normalize_dev  mean = sum/count, inv_std = 1/sqrt(sumsq/count - mean^2 + eps)  (biased variance);
+ *                               y = (x - mean) * (gamma * inv_std) + beta;  running_mean / running_inv_std (nullable) are
+ *                               updated in place: r <- (1 - alpha) r + alpha * batch value.  lasagne: eps 1e-4, alpha 0.1.
+ * ian_minibatch_discrim_dev     MinibatchLayer.get_output_for(init=False) of reference layers.py:486-524:
+ *                               x (n,d), theta (d,K,P), log_weight_scale (K,P), b (K) -> out (n, d+K) = [x | f]. */
+int ian_bn_batch_stats_dev(ian_handle* h, const float* x, int n, int c, int hw, double* sum, double* sumsq, void* stream);
+int ian_bn_train_normalize_dev(ian_handle* h, const float* x, int n, int c, int hw, const double* sum, const double* sumsq,
+                               double count, const float* gamma /*nullable*/, const float* beta /*nullable*/, float eps,
+                               float alpha, float* running_mean /*nullable*/, float* running_inv_std /*nullable*/, float* y,
+                               void* stream);
+int ian_minibatch_discrim_dev(ian_handle* h, const float* x, int n, int d, const float* theta, const float* log_weight_scale,
+                              const float* b, int num_kernels, int dim_per_kernel, float* out, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------------------- */
 /* Average device time (ms, CUDA events on the launch stream) of the tap-GEMM kernel of layer
  * `layer_name` ("enc_conv2", "dec_conv1", ...) over the launches since the last reset; returns <0 if

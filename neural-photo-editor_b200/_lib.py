@@ -55,6 +55,12 @@ SIGNATURES = {
                                     C.c_void_p]),
     "ian_edit_loop_host": (C.c_int, [_H, _F, _I, _F, C.c_int, C.c_int, C.c_int, C.c_float]),
     "ian_paint_stroke_host": (C.c_int, [_H, _F, _I, _F, C.c_float, C.c_void_p, _F, C.c_void_p, C.c_void_p]),
+    "ian_bn_batch_stats_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ian_bn_train_normalize_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                             C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]),
+    "ian_minibatch_discrim_dev": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]),
     "ian_set_layer_timing": (C.c_int, [_H, C.c_int]),
     "ian_layer_time_ms": (C.c_double, [_H, C.c_char_p, C.c_int]),
 }

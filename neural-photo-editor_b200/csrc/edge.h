@@ -53,6 +53,15 @@ void decout_free_maps(DecOutMaps*);
 int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int n, cudaStream_t st);
 // signal + wait kernels of the peer-memory barrier (flag_ptrs[r] = rank r's flag array, int[8])
 int launch_peer_barrier(float* const* flag_ptrs, int world, int rank, int epoch, cudaStream_t st);
+// training-mode pieces (train_kernels.cu): BatchNorm batch statistics / normalisation, MinibatchLayer forward
+size_t bn_workspace_bytes(int c);
+int launch_bn_batch_stats(const float* x, int n, int c, int hw, double* sum, double* sumsq, void* ws, cudaStream_t st);
+int launch_bn_train_normalize(const float* x, int n, int c, int hw, const double* sum, const double* sumsq, double count,
+                              const float* gamma, const float* beta, float eps, float alpha, float* running_mean,
+                              float* running_inv_std, float* y, void* ws, cudaStream_t st);
+size_t mb_workspace_bytes(int n, int K, int P);
+int launch_minibatch_discrim(const float* x, int n, int d, const float* theta, const float* lws, const float* b, int K, int P,
+                             float* out, void* ws, cudaStream_t st);
 // pipelined all-gather: copy this rank's decoded shard (src, n_floats) into every peer's gather buffer from a small
 // side-stream kernel + free/pushed flag handshake (see decout_tc.cu); returns after enqueueing push + wait kernels
 int launch_peer_push(const float* src, float* const* dsts, float* const* flag_ptrs, long long n_floats, int world, int rank,

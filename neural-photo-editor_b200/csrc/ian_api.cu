@@ -190,6 +190,8 @@ struct ian_handle {
   bool g_done_valid[2] = {false, false};
   int g_last = -1;                             // buffer half of the most recent async step
   int push_ctas = 16;
+  void* train_ws = nullptr;                    // workspace of the training-mode ops (grown on demand)
+  size_t train_ws_bytes = 0;
   long long tickets = 0;
   struct Ticket { int id = -1, n = 0, slot = 0; };
   Ticket inflight[2];          // the two most recent pipelined requests (ian_reconstruct_submit)
@@ -1569,6 +1571,7 @@ int ian_destroy(ian_handle* h) {
   cudaFree(h->conv1_tc_wt); if (h->conv1_maps) conv1_free_maps(h->conv1_maps);
   cudaFree(h->made_w); cudaFree(h->made_b); cudaFree(h->head_taps); cudaFree(h->head_wgb); cudaFree(h->head_wbb);
   cudaFree(h->head_tc_wt);
+  cudaFree(h->train_ws);
   for (auto& v : h->timed) for (auto& t : v) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   if (h->push_stream) { cudaStreamSynchronize(h->push_stream); cudaStreamDestroy(h->push_stream); }
   for (int b = 0; b < 2; ++b) { if (h->g_comp[b]) cudaEventDestroy(h->g_comp[b]); if (h->g_done[b]) cudaEventDestroy(h->g_done[b]); }
@@ -2085,6 +2088,52 @@ int ian_gather_wait_dev(ian_handle* h, float** gathered_out, void* stream) {
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_done[h->g_last], 0));
   *gathered_out = h->gbuf + (size_t)h->g_last * ((size_t)h->gw * h->gn * 12288);
+  return IAN_OK;
+}
+
+// ---- training-mode pieces (the trainers themselves stay the reference's) ------------------------------
+static int ensure_train_ws(ian_handle* h, size_t bytes) {
+  if (bytes <= h->train_ws_bytes) return IAN_OK;
+  if (h->train_ws) { CUDA_TRY(h, cudaDeviceSynchronize()); CUDA_TRY(h, cudaFree(h->train_ws)); h->train_ws = nullptr; h->train_ws_bytes = 0; }
+  CUDA_TRY(h, cudaMalloc(&h->train_ws, bytes));
+  h->train_ws_bytes = bytes;
+  return IAN_OK;
+}
+
+int ian_bn_batch_stats_dev(ian_handle* h, const float* x, int n, int c, int hw, double* sum, double* sumsq, void* stream) {
+  if (!h) return IAN_ERR_INVALID;
+  if (!x || !sum || !sumsq || n < 1 || c < 1 || hw < 1) return fail(h, IAN_ERR_INVALID, "bad argument (n=%d c=%d hw=%d)", n, c, hw);
+  DeviceGuard dg(h->device);
+  int rc = ensure_train_ws(h, bn_workspace_bytes(c));
+  if (rc != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_bn_batch_stats(x, n, c, hw, sum, sumsq, h->train_ws, stream ? (cudaStream_t)stream : h->stream));
+  return IAN_OK;
+}
+
+int ian_bn_train_normalize_dev(ian_handle* h, const float* x, int n, int c, int hw, const double* sum, const double* sumsq,
+                               double count, const float* gamma, const float* beta, float eps, float alpha, float* running_mean,
+                               float* running_inv_std, float* y, void* stream) {
+  if (!h) return IAN_ERR_INVALID;
+  if (!x || !y || !sum || !sumsq || n < 1 || c < 1 || hw < 1 || !(count >= 1.0))
+    return fail(h, IAN_ERR_INVALID, "bad argument (n=%d c=%d hw=%d count=%g)", n, c, hw, count);
+  DeviceGuard dg(h->device);
+  int rc = ensure_train_ws(h, bn_workspace_bytes(c));
+  if (rc != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_bn_train_normalize(x, n, c, hw, sum, sumsq, count, gamma, beta, eps, alpha, running_mean, running_inv_std, y,
+                                          h->train_ws, stream ? (cudaStream_t)stream : h->stream));
+  return IAN_OK;
+}
+
+int ian_minibatch_discrim_dev(ian_handle* h, const float* x, int n, int d, const float* theta, const float* log_weight_scale,
+                              const float* b, int num_kernels, int dim_per_kernel, float* out, void* stream) {
+  if (!h) return IAN_ERR_INVALID;
+  if (!x || !theta || !log_weight_scale || !b || !out || n < 1 || d < 1 || num_kernels < 1 || dim_per_kernel < 1)
+    return fail(h, IAN_ERR_INVALID, "bad argument");
+  DeviceGuard dg(h->device);
+  int rc = ensure_train_ws(h, mb_workspace_bytes(n, num_kernels, dim_per_kernel));
+  if (rc != IAN_OK) return rc;
+  LAUNCH_TRY(h, launch_minibatch_discrim(x, n, d, theta, log_weight_scale, b, num_kernels, dim_per_kernel, out, h->train_ws,
+                                         stream ? (cudaStream_t)stream : h->stream));
   return IAN_OK;
 }
 
