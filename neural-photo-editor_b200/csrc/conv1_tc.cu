@@ -7,7 +7,9 @@
 // straight into the 128B-swizzled K-major layout tcgen05 reads (the same layout TMA would produce), then
 // fence.proxy.async + mbarrier hand it to the MMA warp.  Weights (128 x 80, hi|lo) are TMA-loaded once per CTA.
 // 15 MMAs per tile (5 K-slices x 3 passes), two TMEM accumulator buffers, epilogue = bias + LReLU + re-split + NHWC
-// stores into the a1 activation planes.  Roles: warp 0 weight TMA, warp 1 MMA, warps 2-9 epilogue, warps 10-17 im2col.
+// stores into the a1 activation planes.  Roles: warp 0 weight TMA, warp 1 MMA, warps 2-9 epilogue, warps 10-25 im2col
+// (16 producer warps, four threads per operand row: the expansion is the kernel's critical path -- round 1 ran it on
+// 8 warps at IPC 1.2 with 70 % of the issue slots empty, i.e. latency-bound, so the fix is more warps in flight).
 #include <cstdio>
 #include <cstring>
 
@@ -24,8 +26,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 576;
-constexpr int kProducers = 256;
+constexpr int kProducers = 512;
+constexpr int kThreads = 320 + kProducers;
 constexpr int kChunkPlane = 128 * 64 * 2;          // one 128-row x 64-k bf16 plane: 16 KB
 constexpr int kAStage = 2 * 2 * kChunkPlane;       // 2 K chunks x (hi|lo): 64 KB
 constexpr int kBBytes = 2 * 2 * kChunkPlane;       // weights: 2 K chunks x (hi|lo) x 128 rows: 64 KB
@@ -61,13 +63,17 @@ __device__ __forceinline__ void put_unit(uint8_t* stage, const float* patch, int
   *reinterpret_cast<uint4*>(base + kChunkPlane) = *reinterpret_cast<const uint4*>(lo);
 }
 
-template <int H>
-__device__ __forceinline__ void build_half(uint8_t* stage, const float* patch, int m, int r, int c) {
-  put_unit<H * 40 + 0>(stage, patch, m, r, c);
-  put_unit<H * 40 + 8>(stage, patch, m, r, c);
-  put_unit<H * 40 + 16>(stage, patch, m, r, c);
-  put_unit<H * 40 + 24>(stage, patch, m, r, c);
-  put_unit<H * 40 + 32>(stage, patch, m, r, c);
+// the 10 sixteen-byte units (K = 80) of an operand row are split 3 | 3 | 2 | 2 over the row's four producer threads
+__device__ __forceinline__ void build_quarter(int quarter, uint8_t* stage, const float* patch, int m, int r, int c) {
+  if (quarter == 0) {
+    put_unit<0>(stage, patch, m, r, c); put_unit<8>(stage, patch, m, r, c); put_unit<16>(stage, patch, m, r, c);
+  } else if (quarter == 1) {
+    put_unit<24>(stage, patch, m, r, c); put_unit<32>(stage, patch, m, r, c); put_unit<40>(stage, patch, m, r, c);
+  } else if (quarter == 2) {
+    put_unit<48>(stage, patch, m, r, c); put_unit<56>(stage, patch, m, r, c);
+  } else {
+    put_unit<64>(stage, patch, m, r, c); put_unit<72>(stage, patch, m, r, c);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -195,12 +201,14 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
       }
     }
   } else {
-    // ===================== im2col producers (warps 10..17) =====================
-    const int pt = threadIdx.x - 320;                   // 0..255
-    const int m = pt >> 1, hsel = pt & 1;
+    // ===================== im2col producers (warps 10..25) =====================
+    const int pt = threadIdx.x - 320;                   // 0..511
+    // quarter-major: the 32 lanes of a warp build the SAME unit group of 32 consecutive rows (no divergence, and the
+    // patch reads of a warp walk consecutive columns)
+    const int quarter = pt >> 7, m = pt & 127;
     const int r = m >> 5, c = m & 31;
     // the patch of tile t+1 is fetched into registers while tile t is being expanded (global latency hidden)
-    constexpr int kPer = (kPatchFloats + kProducers - 1) / kProducers;    // 9 floats per thread
+    constexpr int kPer = (kPatchFloats + kProducers - 1) / kProducers;    // 5 floats per thread
     float pre[kPer];
     auto fetch = [&](int w) {
       const int n = w / kTilesPerImage, p0 = (w % kTilesPerImage) * 4;
@@ -226,9 +234,9 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
 #pragma unroll
       for (int e = 0; e < kPer; ++e)
         if (pt + e * kProducers < kPatchFloats) patch[pt + e * kProducers] = pre[e];
-      asm volatile("bar.sync 2, 256;" ::: "memory");    // patch complete (producer warps only)
+      asm volatile("bar.sync 2, 512;" ::: "memory");    // patch complete (producer warps only)
       if (w + (int)gridDim.x < total) fetch(w + gridDim.x);
-      if (hsel == 0) build_half<0>(stage, patch, m, r, c); else build_half<1>(stage, patch, m, r, c);
+      build_quarter(quarter, stage, patch, m, r, c);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(s));

@@ -21,23 +21,20 @@ int launch_npe_blend(const float* xhat, const uint8_t* recon, const float* error
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st);
 int launch_head_gather(const float* tt, int tt_is_bf16, const int* taps, int ntaps, float* ha, int n, cudaStream_t st);
-int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
+int launch_rgb_beta_head(const float* ha, int ha_planar, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
                          float* xhat, float* bsave /*nullable*/, int n, cudaStream_t st);
 // brush gradient through the RGB-Beta head: seed over the box, beta/sigmoid/autoregressive backward into dpre (n,64,64,8),
 // then the im2col operand a2 (n,64,64,256 split planes) of the dense backward GEMM (see edge_kernels.cu)
 int launch_head_bwd(const float* xhat, const float* rg, const float* bsave, const int32_t* boxes, const float* target,
                     int target_is_frame, const int* taps, const float* wgb, const float* wbb, int ntaps, float* dpre,
                     __nv_bfloat16* a2, long long a2_plane, int n, cudaStream_t st);
-// RGB-Beta head on the tensor-core path (head_tc.cu): dense GEMM per (image, conv) + on-chip tap gather -> ha [n][6][4096],
-// then the autoregressive sigmoid/Beta part with R, G in shared memory
+// RGB-Beta head on the tensor-core path (head_tc.cu): dense GEMM per (image, conv) + on-chip tap gather -> ha [n][6][4096]
+// (the autoregressive sigmoid / Beta part stays the three per-pixel kernels of edge_kernels.cu)
 struct HeadMaps;
 HeadMaps* head_build_maps(const __nv_bfloat16* fh4, long long fh4_plane, int n_img, const __nv_bfloat16* wt, long long wt_plane,
                           char* err, int errlen);
 void head_free_maps(HeadMaps*);
-int launch_head_tc(const HeadMaps* maps, const int* dy_start /*[10]*/, const int* dx /*[33]*/, int passes, float* ha, int n,
-                   cudaStream_t st);
-int launch_head_rgb(const float* ha, const int* taps, const float* wgb, const float* wbb, int ntaps, float* xhat, float* rg,
-                    float* bsave, int n, cudaStream_t st);
+int launch_head_tc(const HeadMaps* maps, int passes, float* ha, int n, cudaStream_t st);
 // enc_conv1 on the tensor-core path (conv1_tc.cu): thread-built im2col tile + tcgen05
 struct Conv1Maps;
 Conv1Maps* conv1_build_maps(const __nv_bfloat16* wt, long long wt_plane, char* err, int errlen);

@@ -389,21 +389,29 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const T* __restrict__ 
   *reinterpret_cast<float2*>(o + 4) = make_float2(a[4], a[5]);
 }
 
-__global__ void head_r_kernel(const float* __restrict__ ha, float* __restrict__ rg, long long npix) {
+// ha layouts: interleaved (n,64,64,16) from head_gather (verification path) or planar [n][6][4096] from head_tc_kernel
+__device__ __forceinline__ float2 ha_pair(const float* __restrict__ ha, long long i, int c, int planar) {
+  if (!planar) return *reinterpret_cast<const float2*>(ha + i * 16 + c);
+  const float* p = ha + ((i >> 12) * 6 + c) * 4096 + (i & 4095);
+  return make_float2(__ldg(p), __ldg(p + 4096));
+}
+
+__global__ void head_r_kernel(const float* __restrict__ ha, int planar, float* __restrict__ rg, long long npix) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
-  const float2 a = *reinterpret_cast<const float2*>(ha + i * 16);
+  const float2 a = ha_pair(ha, i, 0, planar);
   float4 o = make_float4(sigmoidf_(a.x), sigmoidf_(a.y), 0.f, 0.f);
   *reinterpret_cast<float4*>(rg + i * 4) = o;            // rg: (n,64,64,4) = [R0,R1,G0,G1]
 }
 
-__global__ void head_g_kernel(const float* __restrict__ ha, float* __restrict__ rg, const int* __restrict__ taps,
+__global__ void head_g_kernel(const float* __restrict__ ha, int planar, float* __restrict__ rg, const int* __restrict__ taps,
                               const float* __restrict__ wgb, int ntaps, int n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
   const long long img = i >> 12;
-  float g0 = ha[i * 16 + 2], g1 = ha[i * 16 + 3];
+  const float2 gin = ha_pair(ha, i, 2, planar);
+  float g0 = gin.x, g1 = gin.y;
   for (int t = 0; t < ntaps; ++t) {
     const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
     if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
@@ -415,14 +423,15 @@ __global__ void head_g_kernel(const float* __restrict__ ha, float* __restrict__ 
   *reinterpret_cast<float2*>(rg + i * 4 + 2) = make_float2(sigmoidf_(g0), sigmoidf_(g1));
 }
 
-__global__ void head_b_out_kernel(const float* __restrict__ ha, const float* __restrict__ rg, const int* __restrict__ taps,
+__global__ void head_b_out_kernel(const float* __restrict__ ha, int planar, const float* __restrict__ rg, const int* __restrict__ taps,
                                   const float* __restrict__ wbb, int ntaps, float* __restrict__ xhat,
                                   float* __restrict__ bsave /*nullable: (n,64,64,2) = B, kept for the brush backward*/, int n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
   const long long img = i >> 12;
-  float b0 = ha[i * 16 + 4], b1 = ha[i * 16 + 5];
+  const float2 bin = ha_pair(ha, i, 4, planar);
+  float b0 = bin.x, b1 = bin.y;
   for (int t = 0; t < ntaps; ++t) {
     const int pp = p + taps[2 * t], qq = q + taps[2 * t + 1];
     if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
@@ -574,13 +583,13 @@ int launch_head_gather(const float* tt, int tt_is_bf16, const int* taps, int nta
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_rgb_beta_head(const float* ha, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
+int launch_rgb_beta_head(const float* ha, int ha_planar, float* rg, const int* taps, const float* wgb, const float* wbb, int ntaps,
                          float* xhat, float* bsave, int n, cudaStream_t st) {
   const long long npix = (long long)n * 4096;
   const unsigned blocks = (unsigned)((npix + 255) / 256);
-  head_r_kernel<<<blocks, 256, 0, st>>>(ha, rg, npix);
-  head_g_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wgb, ntaps, n);
-  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, rg, taps, wbb, ntaps, xhat, bsave, n);
+  head_r_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, npix);
+  head_g_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, taps, wgb, ntaps, n);
+  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, taps, wbb, ntaps, xhat, bsave, n);
   return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 

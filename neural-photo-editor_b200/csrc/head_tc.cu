@@ -9,14 +9,14 @@
 // head_tc_kernel: a work item is (image, conv k in {R, G_a, B_a}).  The CTA streams the image's 32 M tiles (2 rows x 64
 // pixels) through ONE dense GEMM each,  T[pixel][t*2+f] = sum_c h[pixel][c] * Wk[t][f][c]  (N = 66 -> 80, K = 128: no
 // shifts, the feature map is staged exactly once per conv), drains T to shared memory, and every epilogue thread adds
-// the taps that land on ITS 16 output pixels,  ha[p][f] += T[p + off_t][t*2+f],  into registers (taps are sorted by row
-// offset, so a tile contributes to an output row through at most two contiguous column ranges).  No atomics, fixed order.
+// the taps that land on ITS 16 output pixels,  ha[p][f] += T[p + off_t][t*2+f],  into registers (weight rows are sorted by
+// the taps' row offset; the [2,3,4]-scale tap set is analytic, so the gather needs no table).  No atomics, fixed order.
 // Roles as in decout_tc.cu: warp 0 TMA (weights per item, A ring), warp 1 tcgen05 issue (float32 = 3-pass bf16 split,
 // main|cross accumulators; or single pass), warps 2-9 epilogue; two TMEM buffers so tile i+1 multiplies while tile i
 // is gathered.
-//
-// head_rgb_kernel: one CTA per image keeps R and G in shared memory and runs the autoregressive part (sigmoid R; G from
-// 33 taps of R; B from 33 taps of [R,G]; Beta means) in one pass -- three kernels and two HBM round trips before.
+// The autoregressive part (sigmoid R; G from 33 taps of R; B from 33 taps of [R,G]; Beta means) stays the three per-pixel
+// kernels of edge_kernels.cu, reading this kernel's planar output: a one-CTA-per-image version with R and G in shared
+// memory was tried and measured 3x slower (512 CTAs of dependent shared-memory chains vs 2 M independent threads on L2).
 #include <cstdio>
 #include <cstring>
 
@@ -30,17 +30,12 @@ struct HeadMaps {
   CUtensorMap b, b1;   // weights (K=128, 3*80 rows, planes): box {64, 80, planes}
 };
 
-struct HeadTaps {       // taps sorted by dy; tap j reads T column pair j
-  int dy_start[10];     // taps with row offset dy = -4 + i are [dy_start[i], dy_start[i+1])
-  int dx[33];
-};
-
 namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiThreads = 512;              // 16 epilogue warps: the drain + gather is latency-bound, more warps hide it
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int BN = 80;                        // 33 taps x 2 filters = 66, padded to a legal UMMA N
 constexpr int kNT = 33;
 constexpr int kAStages = 3;
@@ -57,8 +52,7 @@ template <int PASSES> struct HeadCfg {
 
 template <int PASSES>
 __global__ void __launch_bounds__(kThreads, 1)
-head_tc_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ HeadTaps taps, float* __restrict__ ha /*[n][6][4096]*/,
-               const int n_img) {
+head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[n][6][4096]*/, const int n_img) {
   using Cfg = HeadCfg<PASSES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -151,26 +145,26 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
     }
   } else {
     // ===================== epilogue: TMEM -> smem T tile -> tap gather into registers =====================
-    const int et = threadIdx.x - 64;                    // 0..255
+    const int et = threadIdx.x - 64;                    // 0..511
     const int ew = warp - 2;
     const int lg = warp & 3;                            // TMEM lane group
-    const int half = ew >> 2;                           // T columns [0,48) or [48,80)
+    const int quarter = ew >> 2;                        // T columns [16*quarter, +16); quarter 0 also takes [64, 80)
     const int row = lg * 32 + lane;                     // T tile row = pixel (pr*64 + q) of input rows 2mt + pr
-    const int q = et & 63, r0 = et >> 6;                // this thread's output pixels: column q, rows r0 + 4*i, i = 0..15
+    const int q = et & 63, r0 = et >> 6;                // this thread's output pixels: column q, rows r0 + 8*i, i = 0..7
     uint32_t t = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n = w / 3, k = w % 3;
-      float acc[16][2];
+      float acc[8][2];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+      for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
       for (int mt = 0; mt < kTilesPerImage; ++mt, ++t) {
         const uint32_t buf = t & 1u, use = t >> 1;
         const uint32_t lane_addr = tmem_base + buf * 256 + ((uint32_t)(lg * 32) << 16);
         mbar_wait(tfull_bar(buf), use & 1u);
         tc_fence_after();
-        const int c_begin = half ? 48 : 0, c_end = half ? 80 : 48;
 #pragma unroll 1
-        for (int cb = c_begin; cb < c_end; cb += 16) {
+        for (int cb = 16 * quarter; cb < 80; cb += 64) {
+          if (cb >= 64 && quarter != 0) break;
           uint32_t vm[16], vc[16];
           __syncwarp();
           tmem_ld16(lane_addr + cb, vm);
@@ -184,33 +178,51 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(buf));     // TMEM buffer free: the next tile's MMAs may start
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // T tile complete (epilogue warps only)
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // T tile complete (epilogue warps only)
 
-        // ha[p][f] += T[(p + dy, q + dx)][j*2 + f] for the taps whose input row p + dy lies in this tile (rows 2mt, 2mt+1)
+        // ha[p][f] += T[(p + dy, q + dx)][j*2 + f] for the taps whose input row p + dy lies in this tile (rows 2mt, 2mt+1).
+        // The scales-[2,3,4] MDC has an analytic tap set (checked on the host against the sorted table): a row offset
+        // dy != 0 belongs to exactly one dilation s = |dy| with dx in {-s, 0, +s} (T columns j0, j0+1, j0+2); dy = 0 has
+        // dx in {-1,0,1,-2,2,-3,3,-4,4} (columns 12..20).  No table look-ups, independent loads per hit.
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int p = r0 + 4 * i;
+        for (int i = 0; i < 8; ++i) {
+          const int p = r0 + 8 * i;
 #pragma unroll
           for (int pr = 0; pr < 2; ++pr) {
-            const int dy = 2 * mt + pr - p;              // the row offset that reaches input row 2mt + pr from p
+            const int dy = 2 * mt + pr - p;              // the row offset that reaches input row 2mt + pr from p (warp-uniform)
             if (dy < -4 || dy > 4) continue;
-            const int j0 = taps.dy_start[dy + 4], j1 = taps.dy_start[dy + 5];
-            for (int j = j0; j < j1; ++j) {
-              const int qq = q + taps.dx[j];
-              if (qq < 0 || qq > 63) continue;           // image border (rows outside the image are simply never a tile)
-              const float* tp = Ts + (pr * 64 + qq) * kTLd + 2 * j;
-              acc[i][0] += tp[0];
-              acc[i][1] += tp[1];
+            const float* trow = Ts + (pr * 64 + q) * kTLd;
+            if (dy != 0) {
+              const int sdil = dy < 0 ? -dy : dy;
+              const int j0 = dy < 0 ? 3 * (dy + 4) : 21 + 3 * (dy - 1);
+              const float* tc0 = trow + 2 * j0;
+              float a0 = tc0[2], a1 = tc0[3];            // dx = 0
+              if (q - sdil >= 0) { a0 += tc0[-sdil * kTLd]; a1 += tc0[-sdil * kTLd + 1]; }          // dx = -s
+              if (q + sdil <= 63) { a0 += tc0[sdil * kTLd + 4]; a1 += tc0[sdil * kTLd + 5]; }       // dx = +s
+              acc[i][0] += a0;
+              acc[i][1] += a1;
+            } else {
+              const float* tc0 = trow + 2 * 12;
+              float a0 = tc0[2], a1 = tc0[3];            // dx = 0 (column 13)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {              // dx = -(e+1) / +(e+1): columns {12,14}, {15,16}, {17,18}, {19,20}
+                const int d = e + 1;
+                const int cm = e == 0 ? 0 : 2 * (2 * e + 1), cp = e == 0 ? 4 : 2 * (2 * e + 2);
+                if (q - d >= 0) { a0 += tc0[-d * kTLd + cm]; a1 += tc0[-d * kTLd + cm + 1]; }
+                if (q + d <= 63) { a0 += tc0[d * kTLd + cp]; a1 += tc0[d * kTLd + cp + 1]; }
+              }
+              acc[i][0] += a0;
+              acc[i][1] += a1;
             }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // T tile consumed: may be overwritten
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // T tile consumed: may be overwritten
       }
       float* o0 = ha + ((long long)n * 6 + 2 * k) * 4096 + q;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        o0[(r0 + 4 * i) * 64] = acc[i][0];
-        o0[4096 + (r0 + 4 * i) * 64] = acc[i][1];
+      for (int i = 0; i < 8; ++i) {
+        o0[(r0 + 8 * i) * 64] = acc[i][0];
+        o0[4096 + (r0 + 8 * i) * 64] = acc[i][1];
       }
     }
   }
@@ -218,67 +230,6 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, const __grid_constant__ He
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
-// ---- autoregressive part: one CTA per image, R and G kept in shared memory ---------------------------------------
-//   R = sig(ha[0:2]);  G = sig(ha[2:4] + MDC_Gb(R));  B = sig(ha[4:6] + MDC_Bb([R,G]));  out_c = 2 a/(a+b+1e-8) - 1
-// taps: [33][2] (dy,dx) in the ORIGINAL tap order of wgb [33][2 out][2 in] / wbb [33][2 out][4 in]
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
-
-constexpr int kRgbThreads = 512;
-
-__global__ void __launch_bounds__(kRgbThreads) head_rgb_kernel(const float* __restrict__ ha /*[n][6][4096]*/, const int* __restrict__ taps,
-                                                               const float* __restrict__ wgb, const float* __restrict__ wbb, int ntaps,
-                                                               float* __restrict__ xhat, float* __restrict__ rg /*(n,4096,4)*/,
-                                                               float* __restrict__ bsave /*nullable (n,4096,2)*/) {
-  extern __shared__ float sm[];
-  float2* R = reinterpret_cast<float2*>(sm);             // [4096]
-  float2* G = R + 4096;                                  // [4096]
-  float* wg = reinterpret_cast<float*>(G + 4096);        // [33*4]
-  float* wb = wg + 33 * 4;                               // [33*8]
-  int* tp = reinterpret_cast<int*>(wb + 33 * 8);         // [33*2]
-  const long long img = blockIdx.x;
-  const float* h = ha + img * 6 * 4096;
-  for (int i = threadIdx.x; i < ntaps * 4; i += kRgbThreads) wg[i] = wgb[i];
-  for (int i = threadIdx.x; i < ntaps * 8; i += kRgbThreads) wb[i] = wbb[i];
-  for (int i = threadIdx.x; i < ntaps * 2; i += kRgbThreads) tp[i] = taps[i];
-  for (int i = threadIdx.x; i < 4096; i += kRgbThreads) R[i] = make_float2(sigmoid_f(h[i]), sigmoid_f(h[4096 + i]));
-  __syncthreads();
-  for (int i = threadIdx.x; i < 4096; i += kRgbThreads) {
-    const int p = i >> 6, q = i & 63;
-    float g0 = h[2 * 4096 + i], g1 = h[3 * 4096 + i];
-    for (int t = 0; t < ntaps; ++t) {
-      const int pp = p + tp[2 * t], qq = q + tp[2 * t + 1];
-      if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
-      const float2 r = R[pp * 64 + qq];
-      const float4 w = *reinterpret_cast<const float4*>(wg + t * 4);     // [out0: in0,in1 | out1: in0,in1]
-      g0 = fmaf(r.x, w.x, fmaf(r.y, w.y, g0));
-      g1 = fmaf(r.x, w.z, fmaf(r.y, w.w, g1));
-    }
-    G[i] = make_float2(sigmoid_f(g0), sigmoid_f(g1));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 4096; i += kRgbThreads) {
-    const int p = i >> 6, q = i & 63;
-    float b0 = h[4 * 4096 + i], b1 = h[5 * 4096 + i];
-    for (int t = 0; t < ntaps; ++t) {
-      const int pp = p + tp[2 * t], qq = q + tp[2 * t + 1];
-      if (pp < 0 || pp > 63 || qq < 0 || qq > 63) continue;
-      const float2 r = R[pp * 64 + qq], g = G[pp * 64 + qq];
-      const float4 w0 = *reinterpret_cast<const float4*>(wb + t * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(wb + t * 8 + 4);
-      b0 = fmaf(r.x, w0.x, fmaf(r.y, w0.y, fmaf(g.x, w0.z, fmaf(g.y, w0.w, b0))));
-      b1 = fmaf(r.x, w1.x, fmaf(r.y, w1.y, fmaf(g.x, w1.z, fmaf(g.y, w1.w, b1))));
-    }
-    const float B0 = sigmoid_f(b0), B1 = sigmoid_f(b1);
-    const float2 r = R[i], g = G[i];
-    *reinterpret_cast<float4*>(rg + (img * 4096 + i) * 4) = make_float4(r.x, r.y, g.x, g.y);
-    if (bsave) *reinterpret_cast<float2*>(bsave + (img * 4096 + i) * 2) = make_float2(B0, B1);
-    float* o = xhat + img * 3 * 4096 + i;
-    o[0] = 2.f * (r.x / (r.x + r.y + 1e-8f)) - 1.f;      // beta_layer (layers.py:408)
-    o[4096] = 2.f * (g.x / (g.x + g.y + 1e-8f)) - 1.f;
-    o[8192] = 2.f * (B0 / (B0 + B1 + 1e-8f)) - 1.f;
-  }
 }
 
 }  // namespace
@@ -316,11 +267,7 @@ HeadMaps* head_build_maps(const __nv_bfloat16* fh4, long long fh4_plane, int n_i
 
 void head_free_maps(HeadMaps* m) { delete m; }
 
-int launch_head_tc(const HeadMaps* maps, const int* dy_start /*[10]*/, const int* dx /*[33]*/, int passes, float* ha, int n,
-                   cudaStream_t st) {
-  HeadTaps tp;
-  for (int i = 0; i < 10; ++i) tp.dy_start[i] = dy_start[i];
-  for (int i = 0; i < 33; ++i) tp.dx[i] = dx[i];
+int launch_head_tc(const HeadMaps* maps, int passes, float* ha, int n, cudaStream_t st) {
   static DeviceOnce attr3, attr1;
   const int dev = cur_device();
   const int total = n * 3;
@@ -331,28 +278,14 @@ int launch_head_tc(const HeadMaps* maps, const int* dy_start /*[10]*/, const int
       if (cudaFuncSetAttribute(head_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<3>::kSmemBytes) != cudaSuccess) return -1;
       attr3.set_done(dev);
     }
-    head_tc_kernel<3><<<grid, kThreads, HeadCfg<3>::kSmemBytes, st>>>(*maps, tp, ha, n);
+    head_tc_kernel<3><<<grid, kThreads, HeadCfg<3>::kSmemBytes, st>>>(*maps, ha, n);
   } else {
     if (!attr1.is_done(dev)) {
       if (cudaFuncSetAttribute(head_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<1>::kSmemBytes) != cudaSuccess) return -1;
       attr1.set_done(dev);
     }
-    head_tc_kernel<1><<<grid, kThreads, HeadCfg<1>::kSmemBytes, st>>>(*maps, tp, ha, n);
+    head_tc_kernel<1><<<grid, kThreads, HeadCfg<1>::kSmemBytes, st>>>(*maps, ha, n);
   }
-  return cudaGetLastError() == cudaSuccess ? 1 : -1;
-}
-
-int launch_head_rgb(const float* ha, const int* taps, const float* wgb, const float* wbb, int ntaps, float* xhat, float* rg,
-                    float* bsave, int n, cudaStream_t st) {
-  static DeviceOnce attr;
-  const int dev = cur_device();
-  const int smem = 2 * 4096 * 8 + 33 * (4 + 8) * 4 + 33 * 2 * 4 + 64;
-  if (!attr.is_done(dev)) {
-    if (cudaFuncSetAttribute(head_rgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-    attr.set_done(dev);
-  }
-  if (ntaps != 33) return -1;
-  head_rgb_kernel<<<n, kRgbThreads, smem, st>>>(ha, taps, wgb, wbb, ntaps, xhat, rg, bsave);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

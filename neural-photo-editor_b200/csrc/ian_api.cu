@@ -783,15 +783,15 @@ int run_head(ian_handle* h, Plan* pl, float* xhat, cudaStream_t st) {
   if (h->path == IAN_PATH_TC) {
     {
       ScopedTimer tm(h, F_HEAD, st);
-      LAUNCH_TRY(h, launch_head_tc(pl->head_maps, h->head_dy_start, h->head_dx, h->passes, pl->ha, pl->n, st));
+      LAUNCH_TRY(h, launch_head_tc(pl->head_maps, h->passes, pl->ha, pl->n, st));
     }
-    LAUNCH_TRY(h, launch_head_rgb(pl->ha, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->rg, pl->bsave, pl->n, st));
+    LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, 1, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->bsave, pl->n, st));
     return IAN_OK;
   }
   int rc;
   if ((rc = run_gemm(h, pl, F_HEAD, st)) != IAN_OK) return rc;
   LAUNCH_TRY(h, launch_head_gather(pl->tt, h->passes == 1 ? 1 : 0, h->head_taps, h->head_ntaps, pl->ha, pl->n, st));
-  LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->bsave, pl->n, st));
+  LAUNCH_TRY(h, launch_rgb_beta_head(pl->ha, 0, pl->rg, h->head_taps, h->head_wgb, h->head_wbb, h->head_ntaps, xhat, pl->bsave, pl->n, st));
   return IAN_OK;
 }
 
@@ -1200,6 +1200,18 @@ int prepare_head(ian_handle* h, int C, const std::vector<float>& scale_below /*B
       }
       h->head_dy_start[9] = pos;
       if (pos != 33) return fail(h, IAN_ERR_STATE, "head taps do not fit the [-4,4] row-offset window");
+      // head_tc.cu's gather uses the analytic form of this table: dy != 0 -> dx in {-|dy|, 0, |dy|}; dy = 0 -> the nine offsets
+      // in the order base 3x3, then dilations 2, 3, 4 (mdc_offsets' insertion order).  Refuse anything else.
+      const int dx0[9] = {-1, 0, 1, -2, 2, -3, 3, -4, 4};
+      for (int dy = -4; dy <= 4; ++dy) {
+        const int j0 = h->head_dy_start[dy + 4], cnt = h->head_dy_start[dy + 5] - j0;
+        bool ok = cnt == (dy == 0 ? 9 : 3) && j0 == (dy < 0 ? 3 * (dy + 4) : dy == 0 ? 12 : 21 + 3 * (dy - 1));
+        for (int e = 0; ok && e < cnt; ++e) {
+          const int a = dy < 0 ? -dy : dy;
+          ok = h->head_dx[j0 + e] == (dy == 0 ? dx0[e] : (e - 1) * a);
+        }
+        if (!ok) return fail(h, IAN_ERR_STATE, "RGB-head tap set differs from the scales-[2,3,4] MDC layout head_tc.cu assumes");
+      }
       std::vector<uint16_t> planes((size_t)2 * 3 * 80 * 128, 0);
       const size_t plane = (size_t)3 * 80 * 128;
       for (int k = 0; k < 3; ++k)

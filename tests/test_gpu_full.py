@@ -81,11 +81,13 @@ def test_flow_model_brush_gradients(npe, which, path):
     """imgrad / imgradRGB (reference API.py:59,64,66-76) on the IANv1.py / IAN.py graphs: backward of the RGB-Beta head, the
     MDC residual blocks and the deconvs, against (a) numeric gradients of the EXECUTED reference (ref_exec_*.npz: g_light,
     g_rgb -- central differences of the reference's own forward) and (b) float64 autograd through the torch restatement on
-    other samples / boxes.  Bound, as max-abs error / max|g|: <= 1e-3 on the executed-reference fixtures; on the batched cases
-    median <= 1e-3 and every sample <= 2e-2 -- IANv1 is a ReLU network, and a pre-activation within ~1e-5 of zero may fall on
-    the other side of the rectifier than in float64 (activations carry 16 significand bits; tests/test_gpu_parity.py module
-    docstring), which moves g by up to ~1 % for that sample.  Measured (profiles/r2_flow_brush_parity.json): tc path <= 6e-4
-    everywhere; simt path 8e-6 on the fixtures, 7e-3 on the 64x17-pixel box of IANv1."""
+    other samples / boxes.  Bound, as max-abs error / max|g|: <= 1e-3 on the executed-reference fixtures and on every batched
+    case of IAN.py (LeakyRectify: measured <= 6e-4 tc, <= 4.5e-4 simt).  IANv1 is a ReLU network: a pre-activation within
+    ~1e-5 of zero may fall on the other side of the rectifier than in float64 (activations carry 16 significand bits;
+    tests/test_gpu_parity.py module docstring), and one such unit inside the brush footprint moves g by 0.3-1 %.
+    tools/diag_flow_grad.py (profiles/r2_diag_flow_grad.log) shows it is per (sample, box) and hits BOTH CUDA paths, each on
+    different cases, with everything else at 1e-5 -- so for IANv1 the batched bound is: every case <= 2e-2 and the unflipped
+    cases (at least one of the six) <= 1e-4."""
     import json
     import torch
     from oracle import ian_torch as ot
@@ -117,7 +119,10 @@ def test_flow_model_brush_gradients(npe, which, path):
             rec["rgb_%d" % k] = _rel(g_rgb[k:k + 1], ot.imgradRGB(P64, b[0], b[1], b[2], b[3], fr, zt, decode_fn=dec).numpy())
             rec["light_%d" % k] = _rel(g_light[k:k + 1], ot.imgrad(P64, b[0], b[1], b[2], b[3], zt, decode_fn=dec).numpy())
         batched = [v for k, v in rec.items() if not k.startswith("fixture")]
-        assert np.median(batched) <= 1e-3 and max(batched) <= 2e-2, rec
+        if which == "full":
+            assert max(batched) <= 1e-3, rec
+        else:
+            assert max(batched) <= 2e-2 and min(batched) <= 1e-4, rec
         # the NPE step rule on this graph: two edit steps equal two manual gradient steps
         z2 = m.edit_steps(zb, boxes, rgb, n_steps=2, weight=0.05)
         zm = zb.copy()
