@@ -102,8 +102,8 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
       mbar_wait(b_bar, 0);
       uint32_t i = 0, t = 0;
@@ -119,17 +119,21 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant_
           const uint32_t sa = a_base + s * kAStage, sb = b_base + c * kBChunk;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + 128 * 64 * 2);
           const uint64_t b_hi = make_sw128_desc(sb), b_lo = make_sw128_desc(sb + BN * 64 * 2);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);
-            const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-            umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-            umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);
+              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+              umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+              umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+              umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));
           }
-          umma_commit(empty_bar(s));
+          __syncwarp();
         }
-        umma_commit(tfull_bar(buf));
+        if (elect_one_sync()) umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
     }
   } else {
@@ -246,7 +250,11 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) peer_push_kernel(const PushArgs a) {
+// Footprint: the push runs NEXT TO the persistent tensor kernels of the following step (1 CTA per SM, 168 registers x 320
+// threads, or 72 x 832 for enc_conv1), so a push CTA must fit in what they leave free -- 128 threads, <= 40 registers, no
+// shared memory -- or it would hold an SM back from a statically scheduled persistent kernel (measured: +57 us on
+// enc_conv2 with 256-thread / 60-register push CTAs).
+__global__ void __launch_bounds__(128, 12) peer_push_kernel(const PushArgs a) {
   int* my_flags = a.flags[a.rank];
   if (blockIdx.x == 0 && threadIdx.x < a.world && (int)threadIdx.x != a.rank) {
     __threadfence_system();
@@ -298,7 +306,7 @@ int launch_peer_push(const float* src, float* const* dsts, float* const* flag_pt
   PushArgs a;
   a.src = src; a.n_vec = n_floats / 4; a.world = world; a.rank = rank; a.step = step;
   for (int d = 0; d < world; ++d) { a.dst[d] = dsts[d]; a.flags[d] = reinterpret_cast<int*>(flag_ptrs[d]); }
-  peer_push_kernel<<<ctas, 256, 0, st>>>(a);
+  peer_push_kernel<<<ctas, 128, 0, st>>>(a);
   peer_wait_pushed_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const int*>(flag_ptrs[rank]), world, step);
   return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

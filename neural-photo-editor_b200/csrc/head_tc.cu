@@ -107,8 +107,8 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16_m128(BN);
       uint32_t i = 0, t = 0, it = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
@@ -126,21 +126,26 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
             const uint32_t sa = a_base + s * Cfg::kAStage, sb = b_base + c * Cfg::kBChunk;
             const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + 128 * 64 * 2);
             const uint64_t b_hi = make_sw128_desc(sb), b_lo = make_sw128_desc(sb + BN * 64 * 2);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);
-              const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
-              umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-              if (PASSES == 3) {
-                umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-                umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);
+                const uint32_t acc = (c > 0 || k > 0) ? 1u : 0u;
+                umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+                if (PASSES == 3) {
+                  umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+                  umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+                }
               }
+              umma_commit(empty_bar(s));
             }
-            umma_commit(empty_bar(s));
+            __syncwarp();
           }
-          umma_commit(tfull_bar(buf));
+          if (elect_one_sync()) umma_commit(tfull_bar(buf));
+          __syncwarp();
         }
-        umma_commit(bempty_bar);                         // weights of this item no longer read once these MMAs retire
+        if (elect_one_sync()) umma_commit(bempty_bar);   // weights of this item no longer read once these MMAs retire
+        __syncwarp();
       }
     }
   } else {

@@ -168,6 +168,7 @@ struct ian_handle {
   int sk_epoch = 0;
   bool streamk = true;
   bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
+  bool tc2_bf16 = false;       // bf16 mode on 256 x 256 pair tiles (IAN_TC2_BF16=1; measured slower than the one-CTA kernel)
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
   int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
@@ -189,7 +190,7 @@ struct ian_handle {
   cudaEvent_t g_comp[2] = {nullptr, nullptr}, g_done[2] = {nullptr, nullptr};
   bool g_done_valid[2] = {false, false};
   int g_last = -1;                             // buffer half of the most recent async step
-  int push_ctas = 16;
+  int push_ctas = 32;
   void* train_ws = nullptr;                    // workspace of the training-mode ops (grown on demand)
   size_t train_ws_bytes = 0;
   long long tickets = 0;
@@ -740,9 +741,11 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
   } else {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
-    // pair kernel: float32-split mode always (256 x 128 tiles); bf16 mode only with 256 x 256 tiles (Cout % 256 == 0) --
-    // measured: 256 x 128 single-pass tiles lose to the one-CTA kernel's 128 x 256 / paired-M tiles (smem port bound)
-    const bool pair = pl->maps2[l] && (h->passes == 3 || (g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
+    // pair kernel: float32-split mode (256 x 128 tiles, double-buffered main|cross accumulators).  In bf16 mode the one-CTA
+    // kernel already double-buffers (one accumulator) and measured faster than both pair shapes (256 x 128: 24 KB stages too
+    // short for the TMA latency; 256 x 256: 7-10 % slower on enc_conv2-4), so single-pass layers stay on it unless
+    // IAN_TC2_BF16=1 asks for the 256 x 256 pair tiles.
+    const bool pair = pl->maps2[l] && (h->passes == 3 || (h->tc2_bf16 && g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
     if (pair) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
     else LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
@@ -1469,6 +1472,7 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   if (const char* c = getenv("IAN_STREAMK")) h->streamk = atoi(c) != 0;
   if (const char* c = getenv("IAN_SPLITK")) h->splitk = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2")) h->tc2 = atoi(c) != 0;
+  if (const char* c = getenv("IAN_TC2_BF16")) h->tc2_bf16 = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_MIN")) { int v = atoi(c); if (v > 0) h->tc2_min_tiles = v; }
   if (const char* c = getenv("IAN_TC2_SKIP")) h->tc2_skip = std::string(",") + c + ",";
   if (const char* c = getenv("IAN_GRAPHS")) h->graphs = atoi(c) != 0;

@@ -42,7 +42,7 @@ using namespace tc;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 320;                         // producer, MMA, 8 epilogue warps
+
 
 constexpr int kEpiWarps = 8;
 
@@ -50,7 +50,7 @@ constexpr int kEpiWarps = 8;
 // PASSES = 1: plain bf16 (BASELINE configs[2]): hi planes only, 1 MMA per K slice, one accumulator.
 // MT = M tiles (128 pixels each) per work item sharing ONE weight tile: MT = 2 turns the Cout = 128 layers from
 // operand-feed-bound (64 KB of smem fill per 128x128x64 MMA block) into the 128x256-equivalent intensity.
-template <int BN, int PASSES, int MT> struct TcCfg {
+template <int BN, int PASSES, int MT, int EW = 8> struct TcCfg {
   static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
   static constexpr int kATileBytes = BM * BK * 2 * kPlanes;
   static constexpr int kBTileBytes = BN * BK * 2 * kPlanes;
@@ -61,7 +61,8 @@ template <int BN, int PASSES, int MT> struct TcCfg {
   static constexpr int kAccCols = MT * kTileCols;              // ... of one buffer
   static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
   static constexpr int kTmemCols = (kAccBufs * kAccCols <= 32) ? 32 : (kAccBufs * kAccCols <= 64) ? 64 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + EW * 1024;
+  static constexpr int kThreadsCta = 64 + 32 * EW;     // producer, MMA, EW epilogue warps
 };
 
 template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() { return tc::make_idesc_bf16_m128(BN); }
@@ -189,10 +190,13 @@ struct WorkIter {
   }
 };
 
-template <int BN, int PASSES, int MT, bool SK>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = epilogue warps: 8, or 16 for the short-K single-pass layers whose epilogue (convert + store of 2 x 128 x 128 outputs) is
+// longer than their main loop -- four warps per TMEM lane group, each draining a quarter of the columns.
+template <int BN, int PASSES, int MT, bool SK, int EW = 8>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcMaps maps, const int total_work) {
-  using Cfg = TcCfg<BN, PASSES, MT>;
+  using Cfg = TcCfg<BN, PASSES, MT, EW>;
+  static_assert(EW == 8 || (EW == 16 && !SK && BN >= 128), "16 epilogue warps: whole-tile schedule, >= 128 columns");
   constexpr int kATileBytes = Cfg::kATileBytes;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -217,7 +221,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kEpiWarps);
+      mbar_init(tempty_bar(b), EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,8 +233,8 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
   const int nchunk = g.Cin / BK;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues) =====================
+    {
       uint32_t i = 0;                                   // running K-step counter across work items
       WorkIter<BN, MT, SK> iter;
       iter.init(g, maps, total_work);
@@ -243,19 +247,23 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           const Tap tap = g.taps[ph.tap_begin + it / nchunk];
           const int c0 = (it % nchunk) * BK;
           mbar_wait(empty_bar(s), par ^ 1u);
-          mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          if (elect_one_sync()) {
+            mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
 #pragma unroll
-          for (int j = 0; j < MT; ++j)
-            tma_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], full_bar(s), sa + j * kATileBytes, c0,
-                        wi.q0[j] + tap.dw, wi.p0[j] + tap.dh, wi.n0[j], 0);
-          tma_load_3d(PASSES == 3 ? &maps.b : &maps.b1, full_bar(s), sa + MT * kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
+            for (int j = 0; j < MT; ++j)
+              tma_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], full_bar(s), sa + j * kATileBytes, c0,
+                          wi.q0[j] + tap.dw, wi.p0[j] + tap.dh, wi.n0[j], 0);
+            tma_load_3d(PASSES == 3 ? &maps.b : &maps.b1, full_bar(s), sa + MT * kATileBytes, c0, tap.wtile * g.Cout + wi.co0, 0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the schedule; one elected lane issues: descriptors stay in
+    // uniform registers instead of an ELECT + R2UR waterfall per UTCHMMA) =====================
+    {
       constexpr uint32_t idesc = make_idesc<BN>();
       uint32_t i = 0, t = 0;
       WorkIter<BN, MT, SK> iter;
@@ -273,34 +281,38 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
           tc_fence_after();
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint64_t b_hi = make_sw128_desc(sa + MT * kATileBytes), b_lo = make_sw128_desc(sa + MT * kATileBytes + BN * BK * 2);
-          const bool first = (it == wi.it0);
+          const uint32_t first = (it == wi.it0) ? 0u : 1u;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            const uint64_t a_hi = make_sw128_desc(sa + j * kATileBytes), a_lo = make_sw128_desc(sa + j * kATileBytes + BM * BK * 2);
-            const uint32_t acc_main = acc_base + j * Cfg::kTileCols, acc_cross = acc_main + BN;
+            for (int j = 0; j < MT; ++j) {
+              const uint64_t a_hi = make_sw128_desc(sa + j * kATileBytes), a_lo = make_sw128_desc(sa + j * kATileBytes + BM * BK * 2);
+              const uint32_t acc_main = acc_base + j * Cfg::kTileCols, acc_cross = acc_main + BN;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 slice, in 16-byte units
-              const uint32_t acc = (!first || k > 0) ? 1u : 0u;
-              umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-              if (PASSES == 3) {
-                umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-                umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)(k * 2);   // 32 bytes per K=16 slice, in 16-byte units
+                const uint32_t acc = k > 0 ? 1u : first;
+                umma_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+                if (PASSES == 3) {
+                  umma_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+                  umma_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+                }
               }
             }
+            umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
           }
-          umma_commit(empty_bar(s));                    // frees the smem stage when these MMAs retire
+          __syncwarp();
         }
-        umma_commit(tfull_bar(buf));                    // accumulators of this work item complete
+        if (elect_one_sync()) umma_commit(tfull_bar(buf));   // accumulators of this work item complete
+        __syncwarp();
       }
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
     constexpr int CH = (BN >= 64) ? 32 : 16;            // columns per tcgen05.ld
-    constexpr int COLS_PER_WARP = (BN >= 64) ? BN / 2 : BN;
+    constexpr int COLS_PER_WARP = (BN >= 64) ? BN / (EW / 4) : BN;
     const int ew = warp - 2;
     const int lg = warp & 3;                            // TMEM lane group this warp may access
-    const int half = ew >> 2;                           // which half of the tile's columns
+    const int half = ew >> 2;                           // which slice (half, or quarter with 16 warps) of the tile's columns
     const bool has_cols = (BN >= 64) || half == 0;
     float* my_stage = stage_ptr + ew * 256;             // [0,128): scale, [128,256): shift of this warp's columns
     // activation as a branch-free a*t + b*|t| (none / LeakyRectify(0.2) / rectify; lasagne forms)
@@ -588,13 +600,13 @@ int tc_num_sms() {
 size_t tc_sk_workspace_floats() { return (size_t)tc_num_sms() * kEpiWarps * 32 * 128; }
 size_t tc_sk_flag_ints() { return (size_t)tc_num_sms() * kEpiWarps; }
 
-template <int BN, int PASSES, int MT, bool SK>
+template <int BN, int PASSES, int MT, bool SK, int EW = 8>
 static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<BN, PASSES, MT>;
+  using Cfg = TcCfg<BN, PASSES, MT, EW>;
   static DeviceOnce attr_set;
   const int dev = cur_device();
   if (!attr_set.is_done(dev)) {
-    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+    if (cudaFuncSetAttribute(tapgemm_tc_kernel<BN, PASSES, MT, SK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return -1;
     attr_set.set_done(dev);
   }
@@ -608,7 +620,7 @@ static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num
     total_work = ((tiles_m + MT - 1) / MT) * (g.Cout / maps->BN) * g.nphase * g.ksplit;
     grid = total_work < num_sms ? total_work : num_sms;
   }
-  tapgemm_tc_kernel<BN, PASSES, MT, SK><<<grid, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  tapgemm_tc_kernel<BN, PASSES, MT, SK, EW><<<grid, Cfg::kThreadsCta, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -645,7 +657,8 @@ int launch_tapgemm_tc(const TapGemm& g, const TcMaps* maps, cudaStream_t st) {
   if (g.passes == 1) {
     if (maps->BN == 256) return sk ? launch_one<256, 1, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<256, 1, 1, false>(g, maps, tiles_m, num_sms, st);
     if (maps->BN == 128) {
-      if (pair) return launch_one<128, 1, 2, false>(g, maps, tiles_m, num_sms, st);
+      // short-K single-pass layers (dec_conv4 / dec_conv4a* of IAN.py: 8-50 K steps per tile) are epilogue-bound on 8 warps
+      if (pair) return launch_one<128, 1, 2, false, 16>(g, maps, tiles_m, num_sms, st);
       return sk ? launch_one<128, 1, 1, true>(g, maps, tiles_m, num_sms, st) : launch_one<128, 1, 1, false>(g, maps, tiles_m, num_sms, st);
     }
     return launch_one<16, 1, 1, false>(g, maps, tiles_m, num_sms, st);

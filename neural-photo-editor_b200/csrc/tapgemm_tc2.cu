@@ -265,8 +265,8 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
   const int nchunk = g.Cin / BK;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; whole warp in uniform control flow, one elected lane issues) ==========
+    {
       uint32_t i = 0;
       PairIter<BN, SK> iter;
       iter.init(g, maps, total_work, pair, npairs);
@@ -280,18 +280,24 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
           const int c0 = (it % nchunk) * BK;
           mbar_wait(empty_bar(s), par ^ 1u);            // the pair's MMAs that read this stage (in BOTH CTAs) have retired
           const uint32_t lead_full = mapa_u32(full_bar(s), 0);
-          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          tma2_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], lead_full, sa, c0, wi.q0 + tap.dw, wi.p0 + tap.dh,
-                       wi.n0, 0);
-          tma2_load_3d(PASSES == 3 ? &maps.b : &maps.b1, lead_full, sa + kATileBytes, c0,
-                       tap.wtile * g.Cout + wi.co0 + (int)rank * (BN / 2), 0);
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+            tma2_load_5d(PASSES == 3 ? &maps.a[tap.view] : &maps.a1[tap.view], lead_full, sa, c0, wi.q0 + tap.dw, wi.p0 + tap.dh,
+                         wi.n0, 0);
+            tma2_load_3d(PASSES == 3 ? &maps.b : &maps.b1, lead_full, sa + kATileBytes, c0,
+                         tap.wtile * g.Cout + wi.co0 + (int)rank * (BN / 2), 0);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (rank == 0 && lane == 0) {
+    // The WHOLE warp walks the schedule and waits on the barriers (uniform control flow: descriptors live in uniform
+    // registers); one elected lane issues the MMAs and commits.  At N = 128 a UMMA executes in 64 clocks, so the issue cost
+    // per instruction is on the critical path of this kernel.
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_m256(BN);
       uint32_t i = 0, t = 0;
       PairIter<BN, SK> iter;
@@ -310,19 +316,24 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + BM * BK * 2);
           const uint64_t b_hi = make_sw128_desc(sa + kATileBytes), b_lo = make_sw128_desc(sa + kATileBytes + (BN / 2) * BK * 2);
+          const uint32_t first = (it > wi.it0) ? 1u : 0u;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 2);      // 32 bytes per K=16 slice, in 16-byte units
-            const uint32_t acc = (it > wi.it0 || k > 0) ? 1u : 0u;
-            umma2_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
-            if (PASSES == 3) {
-              umma2_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
-              umma2_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 2);    // 32 bytes per K=16 slice, in 16-byte units
+              const uint32_t acc = (k > 0) ? 1u : first;
+              umma2_bf16(acc_main, a_hi + ko, b_hi + ko, idesc, acc);
+              if (PASSES == 3) {
+                umma2_bf16(acc_cross, a_lo + ko, b_hi + ko, idesc, acc);
+                umma2_bf16(acc_cross, a_hi + ko, b_lo + ko, idesc, 1u);
+              }
             }
+            umma2_commit_mc(empty_bar(s), 3);           // frees the stage in both CTAs when these MMAs retire
           }
-          umma2_commit_mc(empty_bar(s), 3);             // frees the stage in both CTAs when these MMAs retire
+          __syncwarp();
         }
-        umma2_commit_mc(tfull_bar(buf), 3);             // accumulators complete: both CTAs' epilogues may read
+        if (elect_one_sync()) umma2_commit_mc(tfull_bar(buf), 3);   // accumulators complete: both CTAs' epilogues may read
+        __syncwarp();
       }
     }
   } else {

@@ -9,6 +9,20 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  Unlike `lane == 0`, elect.sync tells the compiler that the guarded region runs on
+// exactly one thread of a warp in UNIFORM control flow, so values computed by the whole warp outside it (operand
+// descriptors, barrier addresses, TMA coordinates) stay in uniform registers and tcgen05 / TMA instructions take them
+// directly -- with `if (lane == 0)` around the whole role loop every UTCHMMA cost an ELECT + 5 x R2UR + waterfall branch.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
