@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/ian_b200.h"
 #include "edge.h"
 #include "tapgemm.h"
@@ -191,6 +193,7 @@ struct ian_handle {
   bool g_done_valid[2] = {false, false};
   int g_last = -1;                             // buffer half of the most recent async step
   int push_ctas = 32;
+  int push_mode = 0;                           // 0: copy engines + stream memory ops (no SM is touched); 1: the copy kernel
   void* train_ws = nullptr;                    // workspace of the training-mode ops (grown on demand)
   size_t train_ws_bytes = 0;
   long long tickets = 0;
@@ -1378,6 +1381,27 @@ int prepare_full_decoder(ian_handle* h) {
   return IAN_OK;
 }
 
+// stream memory operations (driver API, fetched through the runtime): the free / pushed flag handshake of the pipelined
+// all-gather runs as cuStreamWriteValue32 / cuStreamWaitValue32 on peer-mapped memory -- no kernel, hence no SM slot
+typedef CUresult (*StreamWrite32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*StreamWait32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct MemOps { StreamWrite32Fn write = nullptr; StreamWait32Fn wait = nullptr; };
+inline const MemOps& memops() {
+  static MemOps m;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *pw = nullptr, *pq = nullptr;
+    cudaDriverEntryPointQueryResult q1, q2;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &pw, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+        cudaGetDriverEntryPoint("cuStreamWaitValue32", &pq, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+      m.write = reinterpret_cast<StreamWrite32Fn>(pw);
+      m.wait = reinterpret_cast<StreamWait32Fn>(pq);
+    }
+  }
+  return m;
+}
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -2079,6 +2103,7 @@ int ian_reconstruct_gather_async_dev(ian_handle* h, const float* x, int n_local,
       CUDA_TRY(h, cudaEventCreateWithFlags(&h->g_done[b], cudaEventDisableTiming));
     }
     if (const char* c = getenv("IAN_PUSH_CTAS")) { int v = atoi(c); if (v >= 1 && v <= 148) h->push_ctas = v; }
+    if (const char* c = getenv("IAN_PUSH")) h->push_mode = !strcmp(c, "kernel") ? 1 : 0;
   }
   const int half_id = h->gcur;
   if (h->g_done_valid[half_id]) CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_done[half_id], 0));   // push of step t-2 has read this half
@@ -2088,8 +2113,36 @@ int ian_reconstruct_gather_async_dev(ian_handle* h, const float* x, int n_local,
   CUDA_TRY(h, cudaEventRecord(h->g_comp[half_id], st));
   CUDA_TRY(h, cudaStreamWaitEvent(h->push_stream, h->g_comp[half_id], 0));
   h->gepoch += 1;
-  LAUNCH_TRY(h, launch_peer_push(g.dsts[h->grank], g.dsts, g.flags, (long long)n_local * 12288, h->gw, h->grank, h->gepoch,
-                                 h->push_ctas, h->push_stream));
+  const MemOps& mo = memops();
+  if (h->push_mode == 0 && mo.write && mo.wait) {
+    // copy engines + stream memory operations: nothing of the push occupies an SM, so the next step's persistent tensor
+    // kernels keep all 148 (a co-resident copy KERNEL held its SMs' shared-memory configuration and cost the first three
+    // tap-GEMMs of the next step +60 % at 8 GPUs).  Order on the side stream: publish free[t] to every peer; per peer wait
+    // for ITS free[t], then DMA the shard into its buffer; publish pushed[t]; wait for everybody's pushed[t].
+    CUstream ps = (CUstream)h->push_stream;
+    const size_t bytes = (size_t)n_local * 12288 * sizeof(float);
+    auto flag = [&](int r, int idx) { return (CUdeviceptr)(uintptr_t)(reinterpret_cast<int*>(g.flags[r]) + idx); };
+    for (int k = 1; k < h->gw; ++k) {
+      const int p = (h->grank + k) % h->gw;
+      if (mo.write(ps, flag(p, 8 + h->grank), (cuuint32_t)h->gepoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+        return fail(h, IAN_ERR_CUDA, "cuStreamWriteValue32(free) failed");
+    }
+    for (int k = 1; k < h->gw; ++k) {
+      const int p = (h->grank + k) % h->gw;
+      if (mo.wait(ps, flag(h->grank, 8 + p), (cuuint32_t)h->gepoch, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(h, IAN_ERR_CUDA, "cuStreamWaitValue32(free) failed");
+      CUDA_TRY(h, cudaMemcpyAsync(g.dsts[p], g.dsts[h->grank], bytes, cudaMemcpyDeviceToDevice, h->push_stream));
+    }
+    for (int p = 0; p < h->gw; ++p)
+      if (mo.write(ps, flag(p, 16 + h->grank), (cuuint32_t)h->gepoch, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+        return fail(h, IAN_ERR_CUDA, "cuStreamWriteValue32(pushed) failed");
+    for (int p = 0; p < h->gw; ++p)
+      if (mo.wait(ps, flag(h->grank, 16 + p), (cuuint32_t)h->gepoch, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return fail(h, IAN_ERR_CUDA, "cuStreamWaitValue32(pushed) failed");
+  } else {
+    LAUNCH_TRY(h, launch_peer_push(g.dsts[h->grank], g.dsts, g.flags, (long long)n_local * 12288, h->gw, h->grank, h->gepoch,
+                                   h->push_ctas, h->push_stream));
+  }
   CUDA_TRY(h, cudaEventRecord(h->g_done[half_id], h->push_stream));
   h->g_done_valid[half_id] = true;
   h->g_last = half_id;

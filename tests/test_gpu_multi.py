@@ -4,7 +4,8 @@ replicated, batch sharded by parallel.shard_bounds, decoded shards all-gathered 
 
 Covered, each against the locally recomputed full batch (every rank can reconstruct every shard: same weights):
   * fused form   (ian_reconstruct_gather_dev): dec_out stores straight into every rank's buffer + flag barrier
-  * pipelined form (ian_reconstruct_gather_async_dev / ian_gather_wait_dev): side-stream push kernel + free/pushed flags
+  * pipelined form (ian_reconstruct_gather_async_dev / ian_gather_wait_dev): side-stream push (copy engines + stream
+    memory operations by default; IAN_PUSH=kernel: the copy kernel) + free/pushed flags
   * shards larger than the 512-image plan chunk
   * RANK SKEW: one rank is delayed by a long device-side sleep before some steps, so a rank that runs ahead would
     overwrite a buffer its peer is still reading if the lifetime contract of include/ian_b200.h did not hold
@@ -79,9 +80,14 @@ def _worker(rank, world, port, q):
             res[tag] = worst
 
         run_case("fused", 6, 6, False)
-        run_case("pipelined", 6, 6, True)
+        run_case("pipelined", 6, 6, True)                 # copy engines + stream memory operations (default push)
         run_case("mixed", 6, 4, False)
         model.close()
+        os.environ["IAN_PUSH"] = "kernel"                 # the copy-KERNEL form of the push (read when the side stream is made)
+        model = pkg.IAN("IAN_simple.py", True, weights=ow.make_simple_weights(0), device=rank)
+        run_case("pipelined_push_kernel", 6, 6, True)
+        model.close()
+        del os.environ["IAN_PUSH"]
         # shards above the 512-image plan chunk, both forms, through the public sharded entry
         model = pkg.IAN("IAN_simple.py", True, weights=ow.make_simple_weights(0), device=rank)
         n = 2 * 520

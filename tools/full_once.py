@@ -5,6 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 from oracle import weights as ow
 pkg = importlib.import_module("neural-photo-editor_b200")
 m = pkg.IAN("IAN.py", True, weights=ow.make_full_weights(0))
+if os.environ.get("FULL_PREC"):
+    m.set_precision(os.environ["FULL_PREC"])
 n = int(os.environ.get("FULL_N", "512"))
 x = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)).cuda()
 z = torch.empty(n, 100, device="cuda"); xh = torch.empty(n, 3, 64, 64, device="cuda")

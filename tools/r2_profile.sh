@@ -5,6 +5,9 @@ B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-edit --no-full --
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv $B > gpurun_out/ncu_l.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tapgemm_tc|decout_tc|conv1_tc' -s 22 -c 11 -o gpurun_out/r2_prof $B > gpurun_out/ncu_f.log 2>&1
 tail -2 gpurun_out/ncu_f.log | cut -c1-300
+# launch lists of the other two measured configurations: edit loop (batch 128), full IAN bf16 (batch 512)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_edit_b128.csv python tools/edit_once.py > /dev/null 2>&1
+FULL_PREC=bf16 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_full_ian_bf16_b512.csv python tools/full_once.py > /dev/null 2>&1
 # sanitizer: small batches through every kernel family (forward, brush, edit, full IAN, v1)
 cat > /tmp/san.py <<'PY'
 import importlib, sys, numpy as np
