@@ -24,8 +24,9 @@
  *     the FFMA verification kernels; IAN_STREAMK=0 disables stream-K scheduling; IAN_GRAPHS=0 disables the CUDA-graph
  *     replay that *_host calls with <= 32 images use; IAN_TC2=0 keeps every layer on the one-CTA tap-GEMM kernel
  *     (default: layers with >= IAN_TC2_MIN (37) whole pair-tiles run on CTA pairs, tcgen05 cta_group::2);
- *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_SPLITK=0 disables split-K (tests); IAN_PUSH_CTAS=<n> sizes the
- *     copy kernel of the pipelined all-gather.
+ *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_TC2_BF16=1 puts bf16-mode layers on 256x256 pair tiles;
+ *     IAN_SPLITK=0 disables split-K (tests); IAN_PUSH=kernel makes the pipelined all-gather push with a copy kernel
+ *     (IAN_PUSH_CTAS=<n> CTAs) instead of copy engines + stream memory operations.
  */
 #ifndef IAN_B200_H_
 #define IAN_B200_H_
@@ -161,9 +162,11 @@ int ian_reconstruct_gather_dev(ian_handle* h, const float* x, int n_local, float
                                void* stream);
 /* Pipelined form of the same all-gather, for streams of batches.  dec_out's peer stores are bound by the NVLink
  * egress (7 x 12.6 MB per GPU and step at 8 x 256 images: ~0.11 ms of link time behind a 0.04 ms kernel), so here the
- * shard is decoded into this rank's own buffer and a small copy kernel on a side stream pushes it to every peer
- * WHILE the next step's tensor kernels run; a free/pushed flag handshake over peer memory orders the buffer reuse
- * across ranks.  ian_reconstruct_gather_async_dev enqueues one step and returns; ian_gather_wait_dev makes `stream`
+ * shard is decoded into this rank's own buffer and a side stream pushes it to every peer WHILE the next step's tensor
+ * kernels run -- by copy engines, with the free/pushed flag handshake that orders the buffer reuse across ranks done as
+ * stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) on peer-mapped flag words, so that no SM is taken
+ * from the persistent tensor kernels (a copy-kernel form exists behind IAN_PUSH=kernel and measured slower for that
+ * reason).  ian_reconstruct_gather_async_dev enqueues one step and returns; ian_gather_wait_dev makes `stream`
  * wait until the most recent step's images of ALL ranks have landed and returns that buffer.  A result must be
  * consumed (in stream order) before the call that submits the step after next.  Steps are collective: every rank
  * calls the same sequence of gather entry points. */

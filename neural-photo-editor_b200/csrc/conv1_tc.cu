@@ -119,8 +119,8 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
       tma_load_3d(&maps.b, b_bar, b_base + 2 * kChunkPlane, 64, 0, 0);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in uniform control flow; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16_m128(128);
       mbar_wait(b_bar, 0);
       uint32_t t = 0;
@@ -131,21 +131,24 @@ conv1_tc_kernel(const __grid_constant__ Conv1Maps maps, const float* __restrict_
         mbar_wait(full_bar(s), use & 1u);
         tc_fence_after();
         const uint32_t sa = a_base + s * kAStage;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < 5; ++ks) {                // K = 80: chunk 0 slices 0..3, chunk 1 slice 0
-          const int chunk = ks >> 2, kk = ks & 3;
-          const uint64_t ko = (uint64_t)(kk * 2);
-          const uint64_t a_hi = make_sw128_desc(sa + chunk * 2 * kChunkPlane) + ko;
-          const uint64_t a_lo = make_sw128_desc(sa + chunk * 2 * kChunkPlane + kChunkPlane) + ko;
-          const uint64_t b_hi = make_sw128_desc(b_base + chunk * 2 * kChunkPlane) + ko;
-          const uint64_t b_lo = make_sw128_desc(b_base + chunk * 2 * kChunkPlane + kChunkPlane) + ko;
-          const uint32_t acc = ks > 0 ? 1u : 0u;
-          umma_bf16(acc_main, a_hi, b_hi, idesc, acc);
-          umma_bf16(acc_cross, a_lo, b_hi, idesc, acc);
-          umma_bf16(acc_cross, a_hi, b_lo, idesc, 1u);
+          for (int ks = 0; ks < 5; ++ks) {              // K = 80: chunk 0 slices 0..3, chunk 1 slice 0
+            const int chunk = ks >> 2, kk = ks & 3;
+            const uint64_t ko = (uint64_t)(kk * 2);
+            const uint64_t a_hi = make_sw128_desc(sa + chunk * 2 * kChunkPlane) + ko;
+            const uint64_t a_lo = make_sw128_desc(sa + chunk * 2 * kChunkPlane + kChunkPlane) + ko;
+            const uint64_t b_hi = make_sw128_desc(b_base + chunk * 2 * kChunkPlane) + ko;
+            const uint64_t b_lo = make_sw128_desc(b_base + chunk * 2 * kChunkPlane + kChunkPlane) + ko;
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            umma_bf16(acc_main, a_hi, b_hi, idesc, acc);
+            umma_bf16(acc_cross, a_lo, b_hi, idesc, acc);
+            umma_bf16(acc_cross, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(s));
         }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(s));
+        __syncwarp();
       }
     }
   } else if (warp < 10) {
