@@ -24,7 +24,7 @@
  *     the FFMA verification kernels; IAN_STREAMK=0 disables stream-K scheduling; IAN_GRAPHS=0 disables the CUDA-graph
  *     replay that *_host calls with <= 32 images use; IAN_TC2=0 keeps every layer on the one-CTA tap-GEMM kernel
  *     (default: layers with >= IAN_TC2_MIN (37) whole pair-tiles run on CTA pairs, tcgen05 cta_group::2);
- *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_TC2_BF16=1 puts bf16-mode layers on 256x256 pair tiles;
+ *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_TC2_BF16=0 keeps bf16-mode layers off the 256x256 pair tiles;
  *     IAN_SPLITK=0 disables split-K (tests); IAN_PUSH=kernel makes the pipelined all-gather push with a copy kernel
  *     (IAN_PUSH_CTAS=<n> CTAs) instead of copy engines + stream memory operations.
  */

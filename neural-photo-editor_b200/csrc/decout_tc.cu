@@ -44,7 +44,7 @@ constexpr int kThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int BN = 80;                       // 25 taps x 3 channels = 75, padded to a legal UMMA N
 constexpr int kAStage = 128 * 64 * 2 * 2;    // one K chunk of the A tile, hi+lo: 32 KB
-constexpr int kAStages = 3;
+constexpr int kAStages = 4;                  // 2 work items of look-ahead (an item is two K chunks): hides the TMA round trip
 constexpr int kBChunk = BN * 64 * 2 * 2;     // one K chunk of the weights, hi+lo: 20 KB
 constexpr int kTLd = 77;                     // T tile row pitch in floats (odd: conflict-free column access)
 constexpr int kTBytes = 128 * kTLd * 4;

@@ -38,12 +38,15 @@ constexpr int kEpiThreads = 512;              // 16 epilogue warps: the drain + 
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int BN = 80;                        // 33 taps x 2 filters = 66, padded to a legal UMMA N
 constexpr int kNT = 33;
-constexpr int kAStages = 3;
 constexpr int kTLd = 67;                      // T row pitch in floats (odd: conflict-free column access)
-constexpr int kTBytes = 2 * 128 * kTLd * 4;   // one T tile per epilogue group
+constexpr int kTBytes = 128 * kTLd * 4;
 constexpr int kTilesPerImage = 32;
 
 template <int PASSES> struct HeadCfg {
+  // the A ring is what hides the TMA round trip: a tile is only two K chunks, so its depth in TILES is kAStages / 2.  Round
+  // 2's first version had 3 stages (1.5 tiles) and ran at ~3.5 k clocks per tile whatever the epilogue did -- TMA-latency
+  // bound.  Now the ring takes all the shared memory left: 4 stages of 32 KB in float32 mode, 8 of 16 KB in bf16 mode.
+  static constexpr int kAStages = PASSES == 3 ? 4 : 8;
   static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
   static constexpr int kAStage = 128 * 64 * 2 * kPlanes;      // one K chunk of an A tile
   static constexpr int kBChunk = BN * 64 * 2 * kPlanes;       // one K chunk of the conv's weights
@@ -54,6 +57,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(kThreads, 1)
 head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[n][6][4096]*/, const int n_img) {
   using Cfg = HeadCfg<PASSES>;
+  constexpr int kAStages = Cfg::kAStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -76,7 +80,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads / 64); }   // 8 warps per group
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads / 32); }
     mbar_init(bfull_bar, 1);
     mbar_init(bempty_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,35 +154,26 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
     }
   } else {
     // ===================== epilogue: TMEM -> smem T tile -> tap gather into registers =====================
-    // Two groups of 8 warps take alternate M tiles (group 0 the even ones = TMEM buffer 0, group 1 the odd ones = buffer 1),
-    // each with its own T tile and named barrier: the drain -> barrier -> gather -> barrier chain of one tile is latency-
-    // bound (a few hundred instructions behind TMEM / shared-memory round trips), so two chains in flight nearly halve
-    // the time per tile.  Each thread accumulates ITS group's contributions to 16 output pixels; the groups' partial sums
-    // are added through shared memory at the end of the item.
     const int et = threadIdx.x - 64;                    // 0..511
-    const int grp = et >> 8, gt = et & 255;             // group, thread within the group
-    const int gw = gt >> 5;                             // warp within the group
+    const int ew = warp - 2;
     const int lg = warp & 3;                            // TMEM lane group
-    const int half = gw >> 2;                           // T columns [0,48) or [48,80)
+    const int quarter = ew >> 2;                        // T columns [16*quarter, +16); quarter 0 also takes [64, 80)
     const int row = lg * 32 + lane;                     // T tile row = pixel (pr*64 + q) of input rows 2mt + pr
-    const int q = gt & 63, r0 = gt >> 6;                // this thread's output pixels: column q, rows r0 + 4*i, i = 0..15
-    float* Tg = Ts + grp * (128 * kTLd);                // this group's T tile
-    const int bar_id = 1 + grp;
-    uint32_t item = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++item) {
+    const int q = et & 63, r0 = et >> 6;                // this thread's output pixels: column q, rows r0 + 8*i, i = 0..7
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int n = w / 3, k = w % 3;
-      float acc[16][2];
+      float acc[8][2];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
-      for (int mt = grp; mt < kTilesPerImage; mt += 2) {
-        const uint32_t t = item * kTilesPerImage + mt;
-        const uint32_t buf = t & 1u, use = t >> 1;       // buf == grp
+      for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; }
+      for (int mt = 0; mt < kTilesPerImage; ++mt, ++t) {
+        const uint32_t buf = t & 1u, use = t >> 1;
         const uint32_t lane_addr = tmem_base + buf * 256 + ((uint32_t)(lg * 32) << 16);
         mbar_wait(tfull_bar(buf), use & 1u);
         tc_fence_after();
-        const int c_begin = half ? 48 : 0, c_end = half ? 80 : 48;
 #pragma unroll 1
-        for (int cb = c_begin; cb < c_end; cb += 16) {
+        for (int cb = 16 * quarter; cb < 80; cb += 64) {
+          if (cb >= 64 && quarter != 0) break;
           uint32_t vm[16], vc[16];
           __syncwarp();
           tmem_ld16(lane_addr + cb, vm);
@@ -187,25 +182,25 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (cb + j < 2 * kNT)
-              Tg[row * kTLd + cb + j] = PASSES == 3 ? __uint_as_float(vm[j]) + __uint_as_float(vc[j]) : __uint_as_float(vm[j]);
+              Ts[row * kTLd + cb + j] = PASSES == 3 ? __uint_as_float(vm[j]) + __uint_as_float(vc[j]) : __uint_as_float(vm[j]);
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(buf));     // TMEM buffer free: the tile after next may start multiplying
-        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // this group's T tile complete
+        if (lane == 0) mbar_arrive(tempty_bar(buf));     // TMEM buffer free: the next tile's MMAs may start
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // T tile complete (epilogue warps only)
 
         // ha[p][f] += T[(p + dy, q + dx)][j*2 + f] for the taps whose input row p + dy lies in this tile (rows 2mt, 2mt+1).
         // The scales-[2,3,4] MDC has an analytic tap set (checked on the host against the sorted table): a row offset
         // dy != 0 belongs to exactly one dilation s = |dy| with dx in {-s, 0, +s} (T columns j0, j0+1, j0+2); dy = 0 has
         // dx in {-1,0,1,-2,2,-3,3,-4,4} (columns 12..20).  No table look-ups, independent loads per hit.
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int p = r0 + 4 * i;
+        for (int i = 0; i < 8; ++i) {
+          const int p = r0 + 8 * i;
 #pragma unroll
           for (int pr = 0; pr < 2; ++pr) {
             const int dy = 2 * mt + pr - p;              // the row offset that reaches input row 2mt + pr from p (warp-uniform)
             if (dy < -4 || dy > 4) continue;
-            const float* trow = Tg + (pr * 64 + q) * kTLd;
+            const float* trow = Ts + (pr * 64 + q) * kTLd;
             if (dy != 0) {
               const int sdil = dy < 0 ? -dy : dy;
               const int j0 = dy < 0 ? 3 * (dy + 4) : 21 + 3 * (dy - 1);
@@ -230,24 +225,14 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
             }
           }
         }
-        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");   // this group's T tile consumed: may be overwritten
+        asm volatile("bar.sync 1, 512;" ::: "memory");   // T tile consumed: may be overwritten
       }
-      // group 1 hands its partial sums to group 0 through its own (now idle) T tile: [16][2][256] floats = 32 KB <= 34 KB
-      if (grp == 1) {
+      float* o0 = ha + ((long long)n * 6 + 2 * k) * 4096 + q;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { Tg[(2 * i) * 256 + gt] = acc[i][0]; Tg[(2 * i + 1) * 256 + gt] = acc[i][1]; }
+      for (int i = 0; i < 8; ++i) {
+        o0[(r0 + 8 * i) * 64] = acc[i][0];
+        o0[4096 + (r0 + 8 * i) * 64] = acc[i][1];
       }
-      asm volatile("bar.sync 3, 512;" ::: "memory");
-      if (grp == 0) {
-        const float* Tp = Ts + 128 * kTLd;
-        float* o0 = ha + ((long long)n * 6 + 2 * k) * 4096 + q;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          o0[(r0 + 4 * i) * 64] = acc[i][0] + Tp[(2 * i) * 256 + gt];
-          o0[4096 + (r0 + 4 * i) * 64] = acc[i][1] + Tp[(2 * i + 1) * 256 + gt];
-        }
-      }
-      asm volatile("bar.sync 3, 512;" ::: "memory");     // group 1's T tile is free again
     }
   }
 

@@ -170,7 +170,7 @@ struct ian_handle {
   int sk_epoch = 0;
   bool streamk = true;
   bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
-  bool tc2_bf16 = false;       // bf16 mode on 256 x 256 pair tiles (IAN_TC2_BF16=1; measured slower than the one-CTA kernel)
+  bool tc2_bf16 = true;        // bf16 mode: Cout % 256 == 0 layers on 256 x 256 pair tiles (IAN_TC2_BF16=0: one-CTA kernel)
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
   int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
@@ -744,10 +744,10 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
   } else {
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e0, st));
-    // pair kernel: float32-split mode (256 x 128 tiles, double-buffered main|cross accumulators).  In bf16 mode the one-CTA
-    // kernel already double-buffers (one accumulator) and measured faster than both pair shapes (256 x 128: 24 KB stages too
-    // short for the TMA latency; 256 x 256: 7-10 % slower on enc_conv2-4), so single-pass layers stay on it unless
-    // IAN_TC2_BF16=1 asks for the 256 x 256 pair tiles.
+    // pair kernel: float32-split mode (256 x 128 tiles, double-buffered main|cross accumulators) and, in bf16 mode, the
+    // Cout % 256 == 0 layers on 256 x 256 tiles (32 KB per 512-clock stage instead of 48 KB: the 192 KB ring then covers
+    // ~3 k clocks of TMA latency instead of ~2 k; measured +5 % on enc_conv2-4 once the MMA issue was fixed).  Cout = 128
+    // single-pass layers stay on the one-CTA kernel's paired-M tiles (256 x 128 pair tiles: 24 KB stages, measured slower).
     const bool pair = pl->maps2[l] && (h->passes == 3 || (h->tc2_bf16 && g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
     if (pair) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
     else LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));

@@ -8,6 +8,8 @@ tail -2 gpurun_out/ncu_f.log | cut -c1-300
 # launch lists of the other two measured configurations: edit loop (batch 128), full IAN bf16 (batch 512)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_edit_b128.csv python tools/edit_once.py > /dev/null 2>&1
 FULL_PREC=bf16 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_full_ian_bf16_b512.csv python tools/full_once.py > /dev/null 2>&1
+# --set full of the full-IAN bf16 tensor-core kernels (second iteration): what bounds the Cout = 128 layers
+FULL_PREC=bf16 FULL_IT=2 timeout 900 ncu --set full --clock-control none -k regex:'tapgemm_tc|head_tc|conv1_tc' -s 18 -c 18 -o gpurun_out/r2_prof_full python tools/full_once.py > gpurun_out/ncu_full.log 2>&1
 # sanitizer: small batches through every kernel family (forward, brush, edit, full IAN, v1)
 cat > /tmp/san.py <<'PY'
 import importlib, sys, numpy as np
