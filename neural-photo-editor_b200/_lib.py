@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libian_b200.so")
+# IAN_B200_LIB: another in-tree BUILD of the same sources/ABI (tools/r2_ab.sh compares two builds on one box); the
+# default is the library build.py produces.  It is never a different implementation: there is no fallback.
+LIB_PATH = os.environ.get("IAN_B200_LIB") or os.path.join(HERE, "libian_b200.so")
 
 IAN_OK = 0
 IAN_PATH_TC, IAN_PATH_SIMT = 0, 1

@@ -73,6 +73,7 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant_
   const int total = n_img * kItemsPerImage;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();                                      // tapgemm.h: PDL
     for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads / 32); }
     mbar_init(b_bar, 1);
@@ -90,6 +91,7 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant_
       mbar_expect_tx(b_bar, 2 * kBChunk);
       tma_load_3d(&maps.b, b_bar, b_base, 0, 0, 0);
       tma_load_3d(&maps.b, b_bar, b_base + kBChunk, 64, 0, 0);
+      pdl_wait();                                       // the weights above are constants; h3 below is dec_conv3's output
       uint32_t i = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int n = w / kItemsPerImage, p0 = (w % kItemsPerImage) * 2;
@@ -138,6 +140,7 @@ decout_tc_kernel(const __grid_constant__ DecOutMaps maps, const __grid_constant_
     }
   } else {
     // ===================== epilogue: TMEM -> smem T tile -> col2im -> tanh -> NCHW store =====================
+    pdl_wait();                                         // the destinations may still be read by an earlier kernel of the stream
     const int et = threadIdx.x - 64;                    // 0..255
     const int ew = warp - 2;
     const int lg = warp & 3;                            // TMEM lane group
@@ -366,7 +369,7 @@ int launch_dec_out_tc(const DecOutMaps* maps, float* const* dsts, int ndst, int 
   DecOutDst dst;
   dst.n = ndst;
   for (int d = 0; d < ndst; ++d) dst.base[d] = dsts[d];
-  decout_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(*maps, dst, n);
+  if (launch_pdl(decout_tc_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, *maps, dst, n) != cudaSuccess) return -1;
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -37,10 +37,14 @@ void head_free_maps(HeadMaps*);
 int launch_head_tc(const HeadMaps* maps, int passes, float* ha, int n, cudaStream_t st);
 // enc_conv1 on the tensor-core path (conv1_tc.cu): thread-built im2col tile + tcgen05
 struct Conv1Maps;
-Conv1Maps* conv1_build_maps(const __nv_bfloat16* wt, long long wt_plane, char* err, int errlen);
+struct Conv1OutMap;
+// wt: three blocks of [128 cout][64 k] bf16 (hi k<64 | lo k<64 | tail: hi k 64..79, lo k 64..79, zeros)
+Conv1Maps* conv1_build_maps(const __nv_bfloat16* wt, char* err, int errlen);
 void conv1_free_maps(Conv1Maps*);
-int launch_conv1_tc(const Conv1Maps* maps, const float* x, const float* bias, __nv_bfloat16* out, long long plane, int n,
-                    cudaStream_t st);
+// per plan: the TMA-store view of the a1 activation planes the kernel writes
+Conv1OutMap* conv1_build_out_map(__nv_bfloat16* out, long long plane, int n, char* err, int errlen);
+void conv1_free_out_map(Conv1OutMap*);
+int launch_conv1_tc(const Conv1Maps* maps, const Conv1OutMap* omap, const float* x, const float* bias, int n, cudaStream_t st);
 // dec_out on the tensor-core path (decout_tc.cu)
 struct DecOutMaps;
 DecOutMaps* decout_build_maps(const __nv_bfloat16* h3, long long h3_plane, int n_img, const __nv_bfloat16* wt,

@@ -166,6 +166,8 @@ __global__ void __launch_bounds__(256) dec_out_kernel(const __nv_bfloat16* __res
 // head (n,256) fp32: mu at [0,100), logsigma at [100,200) -> z fp32 (n,100) and split planes (n,128)
 __global__ void sample_kernel(const float* __restrict__ head, const float* __restrict__ eps, float* __restrict__ z,
                               __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 128) return;
   const int k = i / 128, j = i % 128;
@@ -185,6 +187,8 @@ __global__ void sample_kernel(const float* __restrict__ head, const float* __res
 
 // z fp32 (n,100) -> split planes (n,128), zero padded
 __global__ void z_to_planes_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 128) return;
   const int k = i / 128, j = i % 128;
@@ -200,7 +204,12 @@ __global__ void z_to_planes_kernel(const float* __restrict__ z, __nv_bfloat16* _
 //   seed[k,co,u,v] = coef * (x_hat - t) * (1 - x_hat^2)  inside box_k (coef = 2/(3*bh*bw)), or
 //                    (1/(3*bh*bw)) * (1 - x_hat^2) for the lighten gradient           (API.py:59,64)
 //   d3[k,a,b,ci]   = scale3[ci] * (h3[k,a,b,ci] > 0) * sum_{co,ki,kj} seed[k,co,2+2a-ki,2+2b-kj] * W[ci][co][ki][kj]
-// one thread per (k, a, b, 4 channels); pixels out of reach of the box write zeros.
+// One block per (sample k, feature-map row a), 8 warps; lane l owns channels 4l..4l+3, warp w the pixel pairs
+// (2j, 2j+1), j = w, w+8.  Only rows / pixels within reach of the box (2a-2 < r2 && 2a+2 >= r1, same for columns: at
+// most 11 x 11 of the 32 x 32 map for NPE's <= 17-pixel brush) do any work: the block stages the 5 seed rows it can touch
+// in shared memory (zero outside the box), every in-reach pixel pair walks the valid taps with warp-uniform control flow
+// (a warp is one pixel pair), and everything else is a coalesced zero fill that does not even read h3.  (Round 2's first
+// form ran one thread per (pixel, 4 channels) over the whole map: 104 us at batch 128, 12 % of an edit step.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) brush_seed_bwd_kernel(const float* __restrict__ xhat, const int32_t* __restrict__ boxes,
                                                              const float* __restrict__ target, int target_is_frame,
@@ -208,59 +217,118 @@ __global__ void __launch_bounds__(256) brush_seed_bwd_kernel(const float* __rest
                                                              const float* __restrict__ scale3,
                                                              const __nv_bfloat16* __restrict__ h3,
                                                              __nv_bfloat16* __restrict__ d3, long long plane, int n) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n * 1024 * 32) return;
-  const int c4 = (int)(idx & 31) * 4;
-  const long long pix = idx >> 5;
-  const int b = (int)(pix & 31), a = (int)((pix >> 5) & 31), k = (int)(pix >> 10);
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
+  __shared__ float sd[3 * 5 * 68];                       // [co][row 2a-2 .. 2a+2][col -2 .. 65]
+  __shared__ __align__(16) float ws[25 * 3 * 128];       // dec_out weights of the valid kernel rows, [tap][co][ci] (in-reach rows only)
+  const int k = blockIdx.x >> 5, a = blockIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // device-resident boxes cannot be validated on the host: clamp to the frame here (never read outside x_hat); an
   // empty box contributes nothing and brush_update_kernel turns its gradient into NaN (mean over an empty slice)
   const int c1 = max(boxes[k * 4 + 0], 0), r1 = max(boxes[k * 4 + 1], 0);
   const int c2 = min(boxes[k * 4 + 2], 64), r2 = min(boxes[k * 4 + 3], 64);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long row_off = (long long)(k * 32 + a) * 32 * 128;   // this row of the map: 32 pixels x 128 channels
   // rows u = 2+2a-ki, ki in 0..4  ->  u in [2a-2, 2a+2]
-  if (r1 < r2 && c1 < c2 && 2 * a + 2 >= r1 && 2 * a - 2 < r2 && 2 * b + 2 >= c1 && 2 * b - 2 < c2) {
-    const float inv = 1.f / (3.f * (float)(r2 - r1) * (float)(c2 - c1));
-    for (int ki = 0; ki < 5; ++ki) {
-      const int u = 2 + 2 * a - ki;
-      if (u < r1 || u >= r2) continue;
-      for (int kj = 0; kj < 5; ++kj) {
-        const int v = 2 + 2 * b - kj;
-        if (v < c1 || v >= c2) continue;
-        const float* wp = wt + ((ki * 5 + kj) * 128 + c4) * 4;
+  const bool row_reach = r1 < r2 && c1 < c2 && 2 * a + 2 >= r1 && 2 * a - 2 < r2;
+  if (!row_reach) {                                      // 8 KB per plane = 512 uint4
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4* oh = reinterpret_cast<uint4*>(d3 + row_off);
+    uint4* ol = reinterpret_cast<uint4*>(d3 + plane + row_off);
+    oh[threadIdx.x] = z4; oh[threadIdx.x + 256] = z4;
+    ol[threadIdx.x] = z4; ol[threadIdx.x + 256] = z4;
+    return;
+  }
+  const float inv = 1.f / (3.f * (float)(r2 - r1) * (float)(c2 - c1));
+  for (int i = threadIdx.x; i < 3 * 5 * 68; i += 256) {
+    const int co = i / 340, rem = i % 340;
+    const int u = 2 * a - 2 + rem / 68, v = rem % 68 - 2;
+    float sdv = 0.f;
+    if (u >= r1 && u < r2 && v >= c1 && v < c2) {
+      const long long xi = ((long long)(k * 3 + co) * 64 + u) * 64 + v;
+      const float xv = xhat[xi];
+      if (target) {
+        const float t = target_is_frame ? target[xi] : target[k * 3 + co];
+        sdv = 2.f * inv * (xv - t);
+      } else {
+        sdv = inv;
+      }
+      sdv *= (1.f - xv * xv);
+    }
+    sd[i] = sdv;
+  }
+  // weights through shared memory: every in-reach pixel walks up to the whole 38 KB table, and from L1/L2 each tap was a
+  // dependent round trip (the first block-per-row form spent 60 % of its samples there: 32 us for the launch)
+  for (int i = threadIdx.x; i < 25 * 128; i += 256) {
+    const int tap = i >> 7, ch = i & 127;
+    const int u = 2 + 2 * a - tap / 5;
+    if (u < r1 || u >= r2) continue;                      // (block-uniform per tap row)
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt) + i);
+    ws[(tap * 3 + 0) * 128 + ch] = w4.x;
+    ws[(tap * 3 + 1) * 128 + ch] = w4.y;
+    ws[(tap * 3 + 2) * 128 + ch] = w4.z;
+  }
+  __syncthreads();
+  const float4 sc = *reinterpret_cast<const float4*>(scale3 + lane * 4);
+  for (int j = warp; j < 16; j += 8) {
+    const int b0 = 2 * j;
+    const bool reach0 = 2 * b0 + 2 >= c1 && 2 * b0 - 2 < c2;
+    const bool reach1 = 2 * b0 + 4 >= c1 && 2 * b0 < c2;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (reach0 || reach1) {
+      for (int ki = 0; ki < 5; ++ki) {
+        const int u = 2 + 2 * a - ki;
+        if (u < r1 || u >= r2) continue;
+        const float* srow = sd + (4 - ki) * 68;
+        for (int kj = 0; kj < 5; ++kj) {
+          const int v0 = 2 + 2 * b0 - kj;                 // pixel b0 reads column v0, pixel b0+1 column v0+2
+          if ((v0 < c1 || v0 >= c2) && (v0 + 2 < c1 || v0 + 2 >= c2)) continue;
+          const float* wp = ws + (ki * 5 + kj) * 3 * 128 + lane * 4;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);          // co = 0, channels 4l .. 4l+3
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 128);    // co = 1
+          const float4 w2 = *reinterpret_cast<const float4*>(wp + 256);    // co = 2
+          const float wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w}, wc[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int co = 0; co < 3; ++co) {
-          const float xv = xhat[((long long)(k * 3 + co) * 64 + u) * 64 + v];
-          float sd;
-          if (target) {
-            const float t = target_is_frame ? target[((long long)(k * 3 + co) * 64 + u) * 64 + v] : target[k * 3 + co];
-            sd = 2.f * inv * (xv - t);
-          } else {
-            sd = inv;
+          for (int q = 0; q < 2; ++q) {
+            const float s0 = srow[v0 + 2 + 2 * q], s1 = srow[340 + v0 + 2 + 2 * q], s2 = srow[680 + v0 + 2 + 2 * q];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                 // per channel: co = 0, 1, 2 in this order (as the first form)
+              acc[q][c] = fmaf(s0, wa[c], acc[q][c]);
+              acc[q][c] = fmaf(s1, wb[c], acc[q][c]);
+              acc[q][c] = fmaf(s2, wc[c], acc[q][c]);
+            }
           }
-          sd *= (1.f - xv * xv);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = fmaf(sd, wp[j * 4 + co], acc[j]);
         }
       }
     }
-  }
-  __align__(8) __nv_bfloat16 hi4[4], lo4[4];
-  const long long off = pix * 128 + c4;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float mk = __bfloat162float(h3[off + j]);
-    const float v = mk > 0.f ? acc[j] * scale3[c4 + j] : 0.f;
-    split_bf16(v, hi4[j], lo4[j]);
+    for (int q = 0; q < 2; ++q) {
+      const long long off = row_off + (long long)(b0 + q) * 128 + lane * 4;
+      uint2 hv = make_uint2(0u, 0u), lv = make_uint2(0u, 0u);
+      if (q ? reach1 : reach0) {
+        const uint2 mraw = *reinterpret_cast<const uint2*>(h3 + off);
+        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(&mraw);
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+        __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float v = __bfloat162float(mk[c]) > 0.f ? acc[q][c] * scv[c] : 0.f;
+          split_bf16(v, hi4[c], lo4[c]);
+        }
+        hv = *reinterpret_cast<uint2*>(hi4);
+        lv = *reinterpret_cast<uint2*>(lo4);
+      }
+      *reinterpret_cast<uint2*>(d3 + off) = hv;
+      *reinterpret_cast<uint2*>(d3 + plane + off) = lv;
+    }
   }
-  *reinterpret_cast<uint2*>(d3 + off) = *reinterpret_cast<uint2*>(hi4);
-  *reinterpret_cast<uint2*>(d3 + plane + off) = *reinterpret_cast<uint2*>(lo4);
 }
 
 // g fp32 (n,128 padded) -> user g (n,100) and/or z update  z <- z - weight*g*(1+c2-c1)  (NPE.py:206-209)
 __global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_t* __restrict__ boxes, float weight,
                                     float* __restrict__ g_out, float* __restrict__ z, __nv_bfloat16* __restrict__ zp,
                                     long long zplane, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 128) return;
   const int k = i / 128, j = i % 128;
@@ -295,6 +363,8 @@ __global__ void brush_update_kernel(const float* __restrict__ gpad, const int32_
 __global__ void __launch_bounds__(128) made_iaf_kernel(const float* __restrict__ z0, const float* __restrict__ mw,
                                                        const float* __restrict__ mb, float* __restrict__ z,
                                                        __nv_bfloat16* __restrict__ zp, long long zplane, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   __shared__ float zs[100];
   __shared__ float us[2][100];
   __shared__ float hs[2][100];
@@ -397,6 +467,8 @@ __device__ __forceinline__ float2 ha_pair(const float* __restrict__ ha, long lon
 }
 
 __global__ void head_r_kernel(const float* __restrict__ ha, int planar, float* __restrict__ rg, long long npix) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const float2 a = ha_pair(ha, i, 0, planar);
@@ -406,6 +478,8 @@ __global__ void head_r_kernel(const float* __restrict__ ha, int planar, float* _
 
 __global__ void head_g_kernel(const float* __restrict__ ha, int planar, float* __restrict__ rg, const int* __restrict__ taps,
                               const float* __restrict__ wgb, int ntaps, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
@@ -426,6 +500,8 @@ __global__ void head_g_kernel(const float* __restrict__ ha, int planar, float* _
 __global__ void head_b_out_kernel(const float* __restrict__ ha, int planar, const float* __restrict__ rg, const int* __restrict__ taps,
                                   const float* __restrict__ wbb, int ntaps, float* __restrict__ xhat,
                                   float* __restrict__ bsave /*nullable: (n,64,64,2) = B, kept for the brush backward*/, int n) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * 4096) return;
   const int q = (int)(i & 63), p = (int)((i >> 6) & 63);
@@ -536,27 +612,25 @@ int launch_dec_out(const __nv_bfloat16* h3, long long plane, const float* wt, fl
 
 int launch_sample(const float* head, const float* eps, float* z, __nv_bfloat16* zp, long long zplane, int n,
                   cudaStream_t st) {
-  sample_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(head, eps, z, zp, zplane, n);
+  if (launch_pdl(sample_kernel, dim3((n * 128 + 255) / 256), dim3(256), 0, st, head, eps, z, zp, zplane, n) != cudaSuccess) return -1;
   return CHECK_LAUNCH();
 }
 
 int launch_z_to_planes(const float* z, __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st) {
-  z_to_planes_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(z, zp, zplane, n);
+  if (launch_pdl(z_to_planes_kernel, dim3((n * 128 + 255) / 256), dim3(256), 0, st, z, zp, zplane, n) != cudaSuccess) return -1;
   return CHECK_LAUNCH();
 }
 
 int launch_brush_seed_bwd(const float* xhat, const int32_t* boxes, const float* target, int target_is_frame,
                           const float* wt, const float* scale3, const __nv_bfloat16* h3, __nv_bfloat16* d3,
                           long long plane, int n, cudaStream_t st) {
-  const long long total = (long long)n * 1024 * 32;
-  brush_seed_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xhat, boxes, target, target_is_frame, wt,
-                                                                         scale3, h3, d3, plane, n);
+  if (launch_pdl(brush_seed_bwd_kernel, dim3((unsigned)n * 32u), dim3(256), 0, st, xhat, boxes, target, target_is_frame, wt, scale3, h3, d3, plane, n) != cudaSuccess) return -1;
   return CHECK_LAUNCH();
 }
 
 int launch_brush_update(const float* gpad, const int32_t* boxes, float weight, float* g_out, float* z,
                         __nv_bfloat16* zp, long long zplane, int n, cudaStream_t st) {
-  brush_update_kernel<<<(n * 128 + 255) / 256, 256, 0, st>>>(gpad, boxes, weight, g_out, z, zp, zplane, n);
+  if (launch_pdl(brush_update_kernel, dim3((n * 128 + 255) / 256), dim3(256), 0, st, gpad, boxes, weight, g_out, z, zp, zplane, n) != cudaSuccess) return -1;
   return CHECK_LAUNCH();
 }
 
@@ -570,7 +644,7 @@ int launch_npe_blend(const float* xhat, const uint8_t* recon, const float* error
 
 int launch_made_iaf(const float* z0, const float* mw, const float* mb, float* z, __nv_bfloat16* zp, long long zplane, int n,
                     cudaStream_t st) {
-  made_iaf_kernel<<<n, 128, 0, st>>>(z0, mw, mb, z, zp, zplane, n);
+  if (launch_pdl(made_iaf_kernel, dim3(n), dim3(128), 0, st, z0, mw, mb, z, zp, zplane, n) != cudaSuccess) return -1;
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
@@ -587,9 +661,9 @@ int launch_rgb_beta_head(const float* ha, int ha_planar, float* rg, const int* t
                          float* xhat, float* bsave, int n, cudaStream_t st) {
   const long long npix = (long long)n * 4096;
   const unsigned blocks = (unsigned)((npix + 255) / 256);
-  head_r_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, npix);
-  head_g_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, taps, wgb, ntaps, n);
-  head_b_out_kernel<<<blocks, 256, 0, st>>>(ha, ha_planar, rg, taps, wbb, ntaps, xhat, bsave, n);
+  if (launch_pdl(head_r_kernel, dim3(blocks), dim3(256), 0, st, ha, ha_planar, rg, npix) != cudaSuccess) return -1;
+  if (launch_pdl(head_g_kernel, dim3(blocks), dim3(256), 0, st, ha, ha_planar, rg, taps, wgb, ntaps, n) != cudaSuccess) return -1;
+  if (launch_pdl(head_b_out_kernel, dim3(blocks), dim3(256), 0, st, ha, ha_planar, rg, taps, wbb, ntaps, xhat, bsave, n) != cudaSuccess) return -1;
   return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 

@@ -79,6 +79,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
   const int total = n_img * 3;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();                                      // tapgemm.h: PDL
     for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), kEpiThreads / 32); }
     mbar_init(bfull_bar, 1);
@@ -90,6 +91,7 @@ head_tc_kernel(const __grid_constant__ HeadMaps maps, float* __restrict__ ha /*[
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                           // prologue done; the feature map / ha below belong to the chain
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -287,13 +289,13 @@ int launch_head_tc(const HeadMaps* maps, int passes, float* ha, int n, cudaStrea
       if (cudaFuncSetAttribute(head_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<3>::kSmemBytes) != cudaSuccess) return -1;
       attr3.set_done(dev);
     }
-    head_tc_kernel<3><<<grid, kThreads, HeadCfg<3>::kSmemBytes, st>>>(*maps, ha, n);
+    if (launch_pdl(head_tc_kernel<3>, dim3(grid), dim3(kThreads), HeadCfg<3>::kSmemBytes, st, *maps, ha, n) != cudaSuccess) return -1;
   } else {
     if (!attr1.is_done(dev)) {
       if (cudaFuncSetAttribute(head_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HeadCfg<1>::kSmemBytes) != cudaSuccess) return -1;
       attr1.set_done(dev);
     }
-    head_tc_kernel<1><<<grid, kThreads, HeadCfg<1>::kSmemBytes, st>>>(*maps, ha, n);
+    if (launch_pdl(head_tc_kernel<1>, dim3(grid), dim3(kThreads), HeadCfg<1>::kSmemBytes, st, *maps, ha, n) != cudaSuccess) return -1;
   }
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -172,6 +172,8 @@ struct ian_handle {
   bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
   bool tc2_bf16 = true;        // bf16 mode: Cout % 256 == 0 layers on 256 x 256 pair tiles (IAN_TC2_BF16=0: one-CTA kernel)
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
+  bool pdl = false;            // programmatic dependent launch along the kernel chains (tapgemm.h; IAN_PDL=1)
+  bool tc2_over_split = true;  // float32 mode: the pair kernel (un-split, stream-K) also takes layers choose_ksplit() would split (IAN_TC2_OVER_SPLIT=0)
   int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
   bool graphs = true;          // replay small-batch host calls as CUDA graphs (IAN_GRAPHS=0 turns it off)
@@ -205,7 +207,7 @@ struct ian_handle {
   DevWeights w[L_COUNT];
   float* conv1_wt = nullptr;   // [75][128]
   float* conv1_b = nullptr;    // [128]
-  __nv_bfloat16* conv1_tc_wt = nullptr;    // [2][128 cout][128 k] bf16 planes, k = c*25+i*5+j (75 used)
+  __nv_bfloat16* conv1_tc_wt = nullptr;    // [3][128 cout][64 k] bf16 blocks (hi | lo | tail), k = c*25+i*5+j (75 used)
   Conv1Maps* conv1_maps = nullptr;
   float* decout_wt = nullptr;  // [25][128][4] fp32 (SIMT forward + brush backward)
   __nv_bfloat16* decout_tc_wt = nullptr;   // [2][80][128] bf16 planes, row = tap*3+co (tensor-core forward)
@@ -249,6 +251,7 @@ int fail(ian_handle* h, int code, const char* fmt, ...) {
 
 #define LAUNCH_TRY(h, expr)                                                                          \
   do {                                                                                               \
+    ian::pdl_flag() = (h)->pdl && !(h)->capturing && !(h)->timing;   /* tapgemm.h: PDL */              \
     int _n = (expr);                                                                                 \
     if (_n < 0) return fail(h, IAN_ERR_CUDA, "%s: launch failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
     (h)->launches += _n;                                                                             \
@@ -276,6 +279,7 @@ struct Plan {
   TcMaps* maps[L_COUNT] = {nullptr};
   Tc2Maps* maps2[L_COUNT] = {nullptr};   // CTA-pair kernel (only for layers with enough whole tiles; see build_pair_maps)
   DecOutMaps* decout_maps = nullptr;
+  Conv1OutMap* conv1_out = nullptr;       // TMA-store view of a1 (conv1_tc.cu)
   HeadMaps* head_maps = nullptr;
   // pipelined host API: double-buffered boundary tensors + events (allocated on first use)
   float *sx[2] = {nullptr, nullptr}, *sz[2] = {nullptr, nullptr}, *sxh[2] = {nullptr, nullptr};
@@ -447,11 +451,15 @@ int alloc_splitk_workspace(ian_handle* h, Plan* pl) {
   return IAN_OK;
 }
 
-// A layer moves to the CTA-pair kernel when it runs whole tiles (no split-K, no channel-major output), its channel
-// counts fit the 256 x 128 pair tile and it has at least tc2_min_tiles pair-tiles (one per SM pair).
+// A layer moves to the CTA-pair kernel when it has no channel-major output, its channel counts fit the 256 x 128 pair
+// tile and it has at least tc2_min_tiles pair-tiles (half of the SM pairs).  A split-K factor that choose_ksplit() picked
+// to fill the one-CTA kernel's wave (37..74 tiles: e.g. the decoder's backward-data layers of the batch-128 edit loop)
+// does not hold a layer back: in float32 mode the pair kernel runs it un-split, balanced by stream-K, without the
+// workspace round trip and the finalize launch (run_gemm); bf16 mode keeps the split one-CTA form.
 int build_pair_maps(ian_handle* h, Plan* pl, int l) {
   const TapGemm& g = pl->g[l];
-  if (!h->tc2 || g.ksplit != 1 || g.out_f32_t || g.Cout % 128 || g.Cin % 64) return IAN_OK;
+  if (!h->tc2 || g.out_f32_t || g.Cout % 128 || g.Cin % 64) return IAN_OK;
+  if (g.ksplit != 1 && !h->tc2_over_split) return IAN_OK;
   if (!h->tc2_skip.empty() && h->tc2_skip.find(std::string(",") + kLayerNames[l] + ",") != std::string::npos) return IAN_OK;
   char err[256] = {0};
   Tc2Maps* m = tc2_build_maps(g, err, sizeof(err));
@@ -644,6 +652,11 @@ int build_plan(ian_handle* h, int n, Plan** out) {
   g[L_ENC_FC1].out = pl->f1.p; g[L_ENC_FC1].out_plane = pl->f1.plane; g[L_ENC_FC1].ksplit = 0;
   set_io(g[L_ENC_HEAD], pl->f1, n, 1, 1, 1024, 1, 1, h->w[L_ENC_HEAD], 1, 1); taps_dense(g[L_ENC_HEAD]);
   g[L_ENC_HEAD].act = ACT_NONE; g[L_ENC_HEAD].out_f32 = pl->head;
+  {                                                       // (both paths: ian_set_path may switch a live handle)
+    char err[256] = {0};
+    pl->conv1_out = conv1_build_out_map(pl->a1.p, pl->a1.plane, n, err, sizeof(err));
+    if (!pl->conv1_out) return fail(h, IAN_ERR_CUDA, "enc_conv1: %s", err);
+  }
   if (full) return build_plan_full(h, pl, out);
   if (v1) return build_plan_v1(h, pl, out);
   // ---- decoder (IAN_simple.py:129-170)
@@ -695,6 +708,7 @@ void free_plan(Plan* pl) {
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps[l]) tc_free_maps(pl->maps[l]);
   for (int l = 0; l < L_COUNT; ++l) if (pl->maps2[l]) tc2_free_maps(pl->maps2[l]);
   if (pl->decout_maps) decout_free_maps(pl->decout_maps);
+  if (pl->conv1_out) conv1_free_out_map(pl->conv1_out);
   if (pl->head_maps) head_free_maps(pl->head_maps);
   for (auto& gs : pl->graph) if (gs.exec) cudaGraphExecDestroy(gs.exec);
   delete pl;
@@ -748,9 +762,14 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     // Cout % 256 == 0 layers on 256 x 256 tiles (32 KB per 512-clock stage instead of 48 KB: the 192 KB ring then covers
     // ~3 k clocks of TMA latency instead of ~2 k; measured +5 % on enc_conv2-4 once the MMA issue was fixed).  Cout = 128
     // single-pass layers stay on the one-CTA kernel's paired-M tiles (256 x 128 pair tiles: 24 KB stages, measured slower).
-    const bool pair = pl->maps2[l] && (h->passes == 3 || (h->tc2_bf16 && g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
-    if (pair) LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
-    else LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
+    const bool pair = pl->maps2[l] && (h->passes == 3 || (g.ksplit == 1 && h->tc2_bf16 && g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
+    if (pair) {
+      g.ksplit = 1;                                         // see build_pair_maps: the pair kernel never splits K
+      g.ws = nullptr;
+      LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
+    } else {
+      LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
+    }
     if (h->timing) CUDA_TRY(h, cudaEventRecord(tm.e1, st));
     if (g.ksplit > 1) LAUNCH_TRY(h, launch_splitk_finalize(g, st));
   }
@@ -764,7 +783,7 @@ int run_encode(ian_handle* h, Plan* pl, const float* x, const float* eps, float*
   {
     ScopedTimer tm(h, T_CONV1, st);
     if (h->path == IAN_PATH_TC)
-      LAUNCH_TRY(h, launch_conv1_tc(h->conv1_maps, x, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
+      LAUNCH_TRY(h, launch_conv1_tc(h->conv1_maps, pl->conv1_out, x, h->conv1_b, n, st));
     else
       LAUNCH_TRY(h, launch_conv1(x, h->conv1_wt, h->conv1_b, pl->a1.p, pl->a1.plane, n, st));
   }
@@ -974,18 +993,25 @@ int prepare_encoder(ian_handle* h) {
     const auto& b = P(h, "enc_conv1.b").data;
     CUDA_TRY(h, cudaMalloc((void**)&h->conv1_b, 128 * 4));
     CUDA_TRY(h, cudaMemcpy(h->conv1_b, b.data(), 128 * 4, cudaMemcpyHostToDevice));
-    // tensor-core form: B[co][k] = W[co][c][i][j] (the reference layout flattened), K padded 75 -> 128, hi|lo planes
-    std::vector<uint16_t> planes(2 * 128 * 128, 0);
+    // tensor-core form: B[co][k] = W[co][c][i][j] (the reference layout flattened), K padded 75 -> 80, as three
+    // [128 cout][64 k] blocks: hi of k < 64 | lo of k < 64 | tail (hi of k 64..79 at columns 0..15, lo at 16..31)
+    std::vector<uint16_t> planes(3 * 128 * 64, 0);
     for (int o = 0; o < 128; ++o)
       for (int k = 0; k < 75; ++k) {
         const uint16_t hi = f2bf(W[o * 75 + k]);
-        planes[o * 128 + k] = hi;
-        planes[128 * 128 + o * 128 + k] = f2bf(W[o * 75 + k] - bf2f(hi));
+        const uint16_t lo = f2bf(W[o * 75 + k] - bf2f(hi));
+        if (k < 64) {
+          planes[o * 64 + k] = hi;
+          planes[128 * 64 + o * 64 + k] = lo;
+        } else {
+          planes[2 * 128 * 64 + o * 64 + (k - 64)] = hi;
+          planes[2 * 128 * 64 + o * 64 + 16 + (k - 64)] = lo;
+        }
       }
     CUDA_TRY(h, cudaMalloc((void**)&h->conv1_tc_wt, planes.size() * 2));
     CUDA_TRY(h, cudaMemcpy(h->conv1_tc_wt, planes.data(), planes.size() * 2, cudaMemcpyHostToDevice));
     char err[256] = {0};
-    h->conv1_maps = conv1_build_maps(h->conv1_tc_wt, 128 * 128, err, sizeof(err));
+    h->conv1_maps = conv1_build_maps(h->conv1_tc_wt, err, sizeof(err));
     if (!h->conv1_maps) return fail(h, IAN_ERR_CUDA, "enc_conv1: %s", err);
   }
   return IAN_OK;
@@ -1497,6 +1523,8 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   if (const char* c = getenv("IAN_SPLITK")) h->splitk = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2")) h->tc2 = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_BF16")) h->tc2_bf16 = atoi(c) != 0;
+  if (const char* c = getenv("IAN_PDL")) h->pdl = atoi(c) != 0;
+  if (const char* c = getenv("IAN_TC2_OVER_SPLIT")) h->tc2_over_split = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_MIN")) { int v = atoi(c); if (v > 0) h->tc2_min_tiles = v; }
   if (const char* c = getenv("IAN_TC2_SKIP")) h->tc2_skip = std::string(",") + c + ",";
   if (const char* c = getenv("IAN_GRAPHS")) h->graphs = atoi(c) != 0;

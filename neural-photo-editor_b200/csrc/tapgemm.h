@@ -41,6 +41,42 @@ struct DeviceOnce {
   void set_done(int dev) { done[dev].store(true, std::memory_order_release); }
 };
 
+// Programmatic dependent launch (PDL).  A step is a chain of 13-15 short kernels on one stream; with plain launches each
+// boundary costs the launch latency plus the next kernel's prologue (barrier init, TMEM allocation, first descriptor
+// fetch) plus the previous kernel's tail, with the SMs idle.  Kernels on the hot chains therefore
+//   * call pdl_trigger() first thing (griddepcontrol.launch_dependents: "my successor may be scheduled as soon as every
+//     CTA of mine has said so or exited" -- for the persistent kernels that means: as my CTAs retire, SM by SM), and
+//   * call pdl_wait() (griddepcontrol.wait: the predecessor grid has COMPLETED and its memory is visible) after their own
+//     prologue and before the first global access that is not a constant weight.  Completion is transitive (a grid cannot
+//     complete before its own wait returned), so one wait orders a kernel after everything earlier on the stream; it also
+//     covers write-after-read on shared scratch (split-K / stream-K workspaces).
+// and are launched through launch_pdl(), which sets cudaLaunchAttributeProgrammaticStreamSerialization when the calling
+// thread's pdl_flag() is on (the handle turns it off while capturing graphs or timing layers).  A kernel launched
+// WITHOUT the attribute is a full stream dependency as ever, and both instructions are no-ops in it: every kernel that is
+// not in the list below (flow backward, training pieces, peer barriers, copies, events) still separates the chain.
+inline bool& pdl_flag() {
+  static thread_local bool on = false;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_flag() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 constexpr int kMaxTaps = 40;
 constexpr int kMaxPhases = 4;
 

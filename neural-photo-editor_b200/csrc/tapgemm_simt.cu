@@ -145,6 +145,8 @@ __global__ void __launch_bounds__(256) tapgemm_simt_kernel(const __grid_constant
 
 // ws[split][pix][Cout] raw accumulators -> sum over splits -> epilogue -> planes / f32.  One thread per 4 channels.
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_constant__ TapGemm g, long long npix) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4 = g.Cout / 4;
   if (idx >= npix * c4) return;
@@ -154,10 +156,77 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const __grid_const
   const int oh = (int)((pix / g.Wout) % g.Hout);
   const float* wp = g.ws + pix * g.Cout + co;
   float4 a = __ldcg(reinterpret_cast<const float4*>(wp));
-  for (int k = 1; k < g.ksplit; ++k) {                     // fixed order: bit-reproducible
+  int k = 1;
+  for (; k + 8 <= g.ksplit; k += 8) {                      // 8 slab loads in flight, added in split order: bit-reproducible
+    float4 b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = __ldcg(reinterpret_cast<const float4*>(wp + (long long)(k + j) * g.ws_slab));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a.x += b[j].x; a.y += b[j].y; a.z += b[j].z; a.w += b[j].w; }
+  }
+  for (; k < g.ksplit; ++k) {
     const float4 b = __ldcg(reinterpret_cast<const float4*>(wp + (long long)k * g.ws_slab));
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   }
+  float ar[4] = {a.x, a.y, a.z, a.w};
+  __align__(8) __nv_bfloat16 hi4[4], lo4[4];
+  __align__(16) float f4[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) epilogue_store(g, ar[j], pix, oh, ow, co + j, hi4, lo4, f4, j);
+  if (g.out) {
+    *reinterpret_cast<uint2*>(g.out + pix * g.Cout + co) = *reinterpret_cast<uint2*>(hi4);
+    *reinterpret_cast<uint2*>(g.out + g.out_plane + pix * g.Cout + co) = *reinterpret_cast<uint2*>(lo4);
+  }
+  if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + pix * g.Cout + co) = *reinterpret_cast<float4*>(f4);
+}
+
+
+// The same for deep splits (ksplit >= 8: the dense layers whose K = 16384 is spread over 18-64 CTAs).  One thread walking
+// 64 slabs is a chain of L2 round trips on 16 thread blocks (18 us for the 128 x 128 output of the brush's dz GEMM); here
+// 8 neighbouring lanes LOAD every 8th slab each (all loads in flight at once) and the values are then added in slab
+// order 0, 1, 2, ... through shuffles -- the same float32 additions in the same order as the one-thread form, so the
+// result is bit-identical to it (a shuffle tree would be a different rounding, and 16-bit activations downstream turn
+// last-bit differences into ReLU-mask flips: DESIGN.md section 3).
+__global__ void __launch_bounds__(256) splitk_finalize8_kernel(const __grid_constant__ TapGemm g, long long npix) {
+  pdl_trigger();
+  pdl_wait();                                           // tapgemm.h: PDL
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x & 7;
+  const int c4 = g.Cout / 4;
+  const long long total = npix * c4;
+  long long idx = gidx >> 3;
+  const bool valid = idx < total;
+  if (!valid) idx = total - 1;                          // keep the whole warp in the shuffles
+  const long long pix = idx / c4;
+  const int co = (int)(idx % c4) * 4;
+  const float* wp = g.ws + pix * g.Cout + co;
+  float4 b[8];                                          // slab r*8 + sub (ksplit <= 64)
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int k = r * 8 + sub;
+    b[r] = k < g.ksplit ? __ldcg(reinterpret_cast<const float4*>(wp + (long long)k * g.ws_slab)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 a;                                             // starts as slab 0
+  a.x = __shfl_sync(0xffffffffu, b[0].x, 0, 8);
+  a.y = __shfl_sync(0xffffffffu, b[0].y, 0, 8);
+  a.z = __shfl_sync(0xffffffffu, b[0].z, 0, 8);
+  a.w = __shfl_sync(0xffffffffu, b[0].w, 0, 8);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    if (r * 8 >= g.ksplit) break;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (r == 0 && j == 0) continue;
+      if (r * 8 + j >= g.ksplit) break;                   // (warp-uniform)
+      a.x += __shfl_sync(0xffffffffu, b[r].x, j, 8);
+      a.y += __shfl_sync(0xffffffffu, b[r].y, j, 8);
+      a.z += __shfl_sync(0xffffffffu, b[r].z, j, 8);
+      a.w += __shfl_sync(0xffffffffu, b[r].w, j, 8);
+    }
+  }
+  if (sub != 0 || !valid) return;
+  const int ow = (int)(pix % g.Wout);
+  const int oh = (int)((pix / g.Wout) % g.Hout);
   float ar[4] = {a.x, a.y, a.z, a.w};
   __align__(8) __nv_bfloat16 hi4[4], lo4[4];
   __align__(16) float f4[4];
@@ -182,7 +251,11 @@ int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st) {
 int launch_splitk_finalize(const TapGemm& g, cudaStream_t st) {
   const long long npix = (long long)g.n_img * g.Hout * g.Wout;
   const long long total = npix * (g.Cout / 4);
-  splitk_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, npix);
+  if (g.ksplit >= 8 && total <= 16384) {                 // few outputs, many slabs (the one-thread form fills <= 64 thread blocks)
+    if (launch_pdl(splitk_finalize8_kernel, dim3((unsigned)((total * 8 + 255) / 256)), dim3(256), 0, st, g, npix) != cudaSuccess) return -1;
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
+  if (launch_pdl(splitk_finalize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, g, npix) != cudaSuccess) return -1;
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -94,12 +94,13 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* dst, long long plane,
       lo[j] = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
     }
   }
-  uint4* oh4 = reinterpret_cast<uint4*>(dst);
-  uint4* ol4 = reinterpret_cast<uint4*>(dst + plane);
+  static_assert(CH % 16 == 0, "an epilogue chunk is a whole number of 32-byte sectors per plane");
+  const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lo);
 #pragma unroll
-  for (int j = 0; j < CH / 8; ++j) {
-    oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
-    if (PASSES == 3) ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+  for (int j = 0; j < CH / 16; ++j) {                    // dst is 32-byte aligned: channel offsets are multiples of CH >= 16
+    tc::st_global_256(dst + 16 * j, h4[2 * j], h4[2 * j + 1]);
+    if (PASSES == 3) tc::st_global_256(dst + plane + 16 * j, l4[2 * j], l4[2 * j + 1]);
   }
 }
 
@@ -215,6 +216,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();                                      // the next kernel of the chain may move in as this grid's CTAs retire
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -230,6 +232,7 @@ tapgemm_tc_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ TcM
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                                           // prologue done; everything below reads / writes activations (tapgemm.h: PDL)
   const int nchunk = g.Cin / BK;
 
   if (warp == 0) {
@@ -620,7 +623,8 @@ static int launch_one(const TapGemm& g, const TcMaps* maps, int tiles_m, int num
     total_work = ((tiles_m + MT - 1) / MT) * (g.Cout / maps->BN) * g.nphase * g.ksplit;
     grid = total_work < num_sms ? total_work : num_sms;
   }
-  tapgemm_tc_kernel<BN, PASSES, MT, SK, EW><<<grid, Cfg::kThreadsCta, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  if (launch_pdl(tapgemm_tc_kernel<BN, PASSES, MT, SK, EW>, dim3(grid), dim3(Cfg::kThreadsCta), Cfg::kSmemBytes, st, g, *maps, total_work) != cudaSuccess)
+    return -1;
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

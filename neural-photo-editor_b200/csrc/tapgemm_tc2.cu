@@ -128,12 +128,13 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16* dst, long long plane
       lo[j] = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
     }
   }
-  uint4* oh4 = reinterpret_cast<uint4*>(dst);
-  uint4* ol4 = reinterpret_cast<uint4*>(dst + plane);
+  static_assert(CH % 16 == 0, "an epilogue chunk is a whole number of 32-byte sectors per plane");
+  const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lo);
 #pragma unroll
-  for (int j = 0; j < CH / 8; ++j) {
-    oh4[j] = reinterpret_cast<const uint4*>(hi)[j];
-    if (PASSES == 3) ol4[j] = reinterpret_cast<const uint4*>(lo)[j];
+  for (int j = 0; j < CH / 16; ++j) {                    // dst is 32-byte aligned: channel offsets are multiples of CH >= 16
+    tc::st_global_256(dst + 16 * j, h4[2 * j], h4[2 * j + 1]);
+    if (PASSES == 3) tc::st_global_256(dst + plane + 16 * j, l4[2 * j], l4[2 * j + 1]);
   }
 }
 
@@ -246,6 +247,7 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();                                      // the next kernel of the chain may move in as this grid's CTAs retire
     for (int s = 0; s < S; ++s) {
       mbar_init(full_bar(s), 1);                        // the leader's arrive.expect_tx; bytes come from both CTAs' TMA
       mbar_init(empty_bar(s), 1);
@@ -263,6 +265,7 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int nchunk = g.Cin / BK;
+  pdl_wait();                                           // prologue done; everything below reads / writes activations (tapgemm.h: PDL)
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; whole warp in uniform control flow, one elected lane issues) ==========
@@ -614,7 +617,8 @@ static int launch_pair(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st) {
     total_work = (int)T;
     pairs = pairs_hw;
   }
-  tapgemm_tc2_kernel<BN, PASSES, SK><<<2 * pairs, kThreads, Cfg::kSmemBytes, st>>>(g, *maps, total_work);
+  if (launch_pdl(tapgemm_tc2_kernel<BN, PASSES, SK>, dim3(2 * pairs), dim3(kThreads), Cfg::kSmemBytes, st, g, *maps, total_work) != cudaSuccess)
+    return -1;
   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
