@@ -172,7 +172,9 @@ struct ian_handle {
   bool splitk = true;          // split-K for small-M layers (IAN_SPLITK=0: whole tiles everywhere; used by tests)
   bool tc2_bf16 = true;        // bf16 mode: Cout % 256 == 0 layers on 256 x 256 pair tiles (IAN_TC2_BF16=0: one-CTA kernel)
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
-  bool pdl = false;            // programmatic dependent launch along the kernel chains (tapgemm.h; IAN_PDL=1)
+  bool coop_finalize = true;   // deep split-K layers: cooperative finalize kernel (IAN_FINALIZE8=0: one thread per output everywhere)
+  bool pdl = true;             // programmatic dependent launch along the kernel chains (tapgemm.h; IAN_PDL=0 turns it off)
+  bool tc2_splitk = true;      // float32 mode: deep-K layers with few tiles split K over the SM pairs in the pair kernel (IAN_TC2_SPLITK=0)
   bool tc2_over_split = true;  // float32 mode: the pair kernel (un-split, stream-K) also takes layers choose_ksplit() would split (IAN_TC2_OVER_SPLIT=0)
   int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
@@ -252,6 +254,7 @@ int fail(ian_handle* h, int code, const char* fmt, ...) {
 #define LAUNCH_TRY(h, expr)                                                                          \
   do {                                                                                               \
     ian::pdl_flag() = (h)->pdl && !(h)->capturing && !(h)->timing;   /* tapgemm.h: PDL */              \
+    ian::coop_finalize_flag() = (h)->coop_finalize;                                                  \
     int _n = (expr);                                                                                 \
     if (_n < 0) return fail(h, IAN_ERR_CUDA, "%s: launch failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
     (h)->launches += _n;                                                                             \
@@ -278,6 +281,7 @@ struct Plan {
   TapGemm g[L_COUNT];
   TcMaps* maps[L_COUNT] = {nullptr};
   Tc2Maps* maps2[L_COUNT] = {nullptr};   // CTA-pair kernel (only for layers with enough whole tiles; see build_pair_maps)
+  int pair_ksplit[L_COUNT] = {0};        // K split the pair kernel runs the layer with (1 = un-split; build_pair_maps)
   DecOutMaps* decout_maps = nullptr;
   Conv1OutMap* conv1_out = nullptr;       // TMA-store view of a1 (conv1_tc.cu)
   HeadMaps* head_maps = nullptr;
@@ -464,8 +468,29 @@ int build_pair_maps(ian_handle* h, Plan* pl, int l) {
   char err[256] = {0};
   Tc2Maps* m = tc2_build_maps(g, err, sizeof(err));
   if (!m) return fail(h, IAN_ERR_CUDA, "layer %s (pair kernel): %s", kLayerNames[l], err);
-  if (tc2_pair_tiles(g, m) < h->tc2_min_tiles) { tc2_free_maps(m); return IAN_OK; }
-  pl->maps2[l] = m;
+  const long long pt = tc2_pair_tiles(g, m);
+  if (pt >= h->tc2_min_tiles) {
+    pl->maps2[l] = m;
+    pl->pair_ksplit[l] = 1;
+    return IAN_OK;
+  }
+  // Few tiles but a deep K (enc_fc1 at batch 256: 8 pair-tiles x 256 K steps): split K over the SM pairs in the pair kernel
+  // too.  The one-CTA kernel's 256-wide float32 tiles leave room for only 2 x 96 KB stages -- the TMA ring covers half of the
+  // load latency and enc_fc1 ran at 35 % tensor activity; the pair kernel's 48 KB stages are four deep.  Same slab /
+  // finalize protocol (the plan's workspace is sized for the one-CTA split, which is never smaller).  Batches above the
+  // graph-replayed sizes only, so the single-image latency path keeps one schedule.
+  if (h->tc2_splitk && g.ksplit > 1 && g.n_img > 32 && (long long)g.n_img * g.Hg * g.Wg >= 256) {
+    int min_it = 1 << 30;
+    for (int p = 0; p < g.nphase; ++p) min_it = std::min(min_it, g.phase[p].ntaps * (g.Cin / 64));
+    int ks = (int)((tc_num_sms() / 2) / pt);
+    ks = std::min(ks, std::min(min_it / 8, g.ksplit));
+    if (ks >= 2 && pt * ks >= h->tc2_min_tiles) {
+      pl->maps2[l] = m;
+      pl->pair_ksplit[l] = ks;
+      return IAN_OK;
+    }
+  }
+  tc2_free_maps(m);
   return IAN_OK;
 }
 
@@ -762,10 +787,12 @@ int run_gemm(ian_handle* h, Plan* pl, int l, cudaStream_t st) {
     // Cout % 256 == 0 layers on 256 x 256 tiles (32 KB per 512-clock stage instead of 48 KB: the 192 KB ring then covers
     // ~3 k clocks of TMA latency instead of ~2 k; measured +5 % on enc_conv2-4 once the MMA issue was fixed).  Cout = 128
     // single-pass layers stay on the one-CTA kernel's paired-M tiles (256 x 128 pair tiles: 24 KB stages, measured slower).
-    const bool pair = pl->maps2[l] && (h->passes == 3 || (g.ksplit == 1 && h->tc2_bf16 && g.Cout % 256 == 0 && tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
+    const int pks = pl->pair_ksplit[l];
+    const bool pair = pl->maps2[l] && (h->passes == 3 || (pks == 1 && g.ksplit == 1 && h->tc2_bf16 && g.Cout % 256 == 0 &&
+                                                          tc2_pair_tiles(g, pl->maps2[l]) / 2 >= h->tc2_min_tiles));
     if (pair) {
-      g.ksplit = 1;                                         // see build_pair_maps: the pair kernel never splits K
-      g.ws = nullptr;
+      g.ksplit = pks;                                       // see build_pair_maps: un-split (1) or the pair kernel's own split
+      if (pks == 1) g.ws = nullptr;
       LAUNCH_TRY(h, launch_tapgemm_tc2(g, pl->maps2[l], st));
     } else {
       LAUNCH_TRY(h, launch_tapgemm_tc(g, pl->maps[l], st));
@@ -1524,6 +1551,8 @@ int ian_create(int model_kind, int device, ian_handle** out) {
   if (const char* c = getenv("IAN_TC2")) h->tc2 = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_BF16")) h->tc2_bf16 = atoi(c) != 0;
   if (const char* c = getenv("IAN_PDL")) h->pdl = atoi(c) != 0;
+  if (const char* c = getenv("IAN_FINALIZE8")) h->coop_finalize = atoi(c) != 0;
+  if (const char* c = getenv("IAN_TC2_SPLITK")) h->tc2_splitk = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_OVER_SPLIT")) h->tc2_over_split = atoi(c) != 0;
   if (const char* c = getenv("IAN_TC2_MIN")) { int v = atoi(c); if (v > 0) h->tc2_min_tiles = v; }
   if (const char* c = getenv("IAN_TC2_SKIP")) h->tc2_skip = std::string(",") + c + ",";

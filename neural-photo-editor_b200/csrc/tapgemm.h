@@ -58,6 +58,12 @@ inline bool& pdl_flag() {
   static thread_local bool on = false;
   return on;
 }
+// split-K finalize: the cooperative (8 lanes per output) form for deep splits; off = the one-thread form everywhere.  Both
+// add the slabs in the same order (tests/test_gpu_parity.py compares them bit for bit); handle-controlled like pdl_flag().
+inline bool& coop_finalize_flag() {
+  static thread_local bool on = true;
+  return on;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -251,7 +251,7 @@ int launch_tapgemm_simt(const TapGemm& g, cudaStream_t st) {
 int launch_splitk_finalize(const TapGemm& g, cudaStream_t st) {
   const long long npix = (long long)g.n_img * g.Hout * g.Wout;
   const long long total = npix * (g.Cout / 4);
-  if (g.ksplit >= 8 && total <= 16384) {                 // few outputs, many slabs (the one-thread form fills <= 64 thread blocks)
+  if (coop_finalize_flag() && g.ksplit >= 8 && total <= 16384) {                 // few outputs, many slabs (the one-thread form fills <= 64 thread blocks)
     if (launch_pdl(splitk_finalize8_kernel, dim3((unsigned)((total * 8 + 255) / 256)), dim3(256), 0, st, g, npix) != cudaSuccess) return -1;
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }

@@ -142,6 +142,7 @@ __device__ __forceinline__ void store_split2(__nv_bfloat16* dst, long long plane
 struct PairWork {
   int phase, co0, it0, it1;
   int n0, p0, q0, mtile;
+  int ks;                       // split-K: which K split of the tile (whole-tile schedule, g.ksplit > 1)
   // stream-K: 0 = whole tile; 1 = contributor (a later part of a tile: raw sums -> this CTA's workspace slot);
   // 2 = finisher (the first part of a tile cut by a pair boundary: adds the parts of pairs pair+1 .. sk_last, in order)
   int sk_role, sk_last;
@@ -201,8 +202,16 @@ struct PairIter {
   __device__ __forceinline__ bool next(const TapGemm& g, const Tc2Maps& maps, int rank, PairWork& wi) {
     if (!SK) {
       if (w >= total) return false;
-      decode_tile<BN>(g, maps, w / per_phase, w % per_phase, rank, wi);
-      wi.it0 = 0; wi.it1 = iters_of(g, wi.phase); wi.sk_role = 0; wi.sk_last = 0;
+      // (phase | K split | pair-tile): split-K layers (g.ksplit > 1, dense layers with few tiles and a deep K) store raw
+      // sums to slab ks of g.ws like the one-CTA kernel; splitk_finalize adds the slabs in split order
+      const int per_phase_k = per_phase * g.ksplit;
+      const int r = w % per_phase_k;
+      decode_tile<BN>(g, maps, w / per_phase_k, r % per_phase, rank, wi);
+      const int ip = iters_of(g, wi.phase);
+      wi.ks = r / per_phase;
+      wi.it0 = (int)((long long)ip * wi.ks / g.ksplit);
+      wi.it1 = (int)((long long)ip * (wi.ks + 1) / g.ksplit);
+      wi.sk_role = 0; wi.sk_last = 0;
       w += stride;
       return true;
     }
@@ -214,6 +223,7 @@ struct PairIter {
     int len = ip - it;
     if (len > end - gi) len = end - gi;
     decode_tile<BN>(g, maps, ph, tile, rank, wi);
+    wi.ks = 0;
     wi.it0 = it; wi.it1 = it + len;
     wi.sk_role = it > 0 ? 1 : (len < ip ? 2 : 0);
     wi.sk_last = wi.sk_role == 2 ? owner(phase_start + tile * ip + ip - 1) : 0;
@@ -433,6 +443,14 @@ tapgemm_tc2_kernel(const __grid_constant__ TapGemm g, const __grid_constant__ Tc
             }
           }
         }
+        if (!SK && g.ksplit > 1) {                       // this K split's slab; the finalize kernel adds them in order
+          if (valid) {
+            float4* wsp = reinterpret_cast<float4*>(g.ws + (long long)wi.ks * g.ws_slab + pix * g.Cout + co);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) __stcg(wsp + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          }
+          continue;
+        }
         if (!valid) continue;
         const long long off = pix * g.Cout + co;
         if (g.out_raw) store_split2<CH, PASSES>(g.out_raw + off, g.out_raw_plane, v);   // pre-BN value (MDBLOCK residual input)
@@ -607,7 +625,7 @@ static int launch_pair(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st) {
       return -1;
     attr_set.set_done(dev);
   }
-  const int tiles = (int)pair_tiles_bn(g, maps, BN);
+  const int tiles = (int)pair_tiles_bn(g, maps, BN) * (SK ? 1 : g.ksplit);
   const int pairs_hw = tc_num_sms() / 2;
   int total_work = tiles, pairs = tiles < pairs_hw ? tiles : pairs_hw;
   if (SK) {                                              // T K-steps, one pair per SM pair, every pair gets T/G of them
@@ -655,7 +673,11 @@ static bool want_streamk_uncached(const TapGemm& g, const Tc2Maps* maps, int bn)
 }
 
 int launch_tapgemm_tc2(const TapGemm& g, const Tc2Maps* maps, cudaStream_t st) {
-  if (g.ksplit != 1 || g.out_f32_t) return -1;
+  if (g.ksplit < 1 || g.out_f32_t) return -1;
+  if (g.ksplit > 1) {                                    // split-K: whole-tile schedule over (K split | pair-tile), float32 mode
+    if (g.passes != 3 || !g.ws) return -1;
+    return launch_pair<128, 3, false>(g, maps, st);
+  }
   if (g.passes == 1) {
     if (maps->BN1 != 256) return -1;                      // Cout = 128 in bf16 mode: one-CTA kernel
     return want_streamk(g, maps, 256) ? launch_pair<256, 1, true>(g, maps, st) : launch_pair<256, 1, false>(g, maps, st);

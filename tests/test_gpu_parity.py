@@ -396,3 +396,40 @@ def test_pair_kernel_equals_one_cta_kernel(npe, weights, monkeypatch):
         one.close()
         pair.close()
         pair_sk.close()
+
+
+def test_pdl_and_coop_finalize_are_bit_identical(npe, weights, monkeypatch):
+    """Two launch-level options must not change a single bit:
+      * programmatic dependent launch along the kernel chains (csrc/tapgemm.h; the default, IAN_PDL=0 turns it off): the
+        next kernel's prologue overlaps the previous kernel's tail, every kernel waits (griddepcontrol.wait) before
+        touching activations -- compared against a handle with plain launches;
+      * IAN_FINALIZE8=0 -- the one-thread split-K finalize instead of the cooperative one (same slab order by construction).
+    Plain launches (graphs off) so that PDL is really in effect; batches that cover split-K layers (1, 5), whole pair tiles
+    and stream-K (160) and the batch-128 edit loop's mix."""
+    monkeypatch.setenv("IAN_GRAPHS", "0")
+    monkeypatch.setenv("IAN_PDL", "0")
+    base = npe.IAN("IAN_simple.py", True, weights=weights)
+    monkeypatch.setenv("IAN_PDL", "1")
+    pdl = npe.IAN("IAN_simple.py", True, weights=weights)
+    monkeypatch.delenv("IAN_PDL")
+    monkeypatch.setenv("IAN_FINALIZE8", "0")
+    seq = npe.IAN("IAN_simple.py", True, weights=weights)
+    monkeypatch.delenv("IAN_FINALIZE8")
+    rng = np.random.default_rng(77)
+    try:
+        for n in (1, 5, 128, 160):
+            x = rng.uniform(-1, 1, (n, 3, 64, 64)).astype(np.float32)
+            z = rng.standard_normal((n, 100)).astype(np.float32)
+            boxes = np.tile(np.array([[9, 4, 26, 21]], np.int32), (n, 1))
+            boxes[::2] = [40, 33, 47, 40]
+            rgb = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+            ref = (base.reconstruct(x, return_z=True), base.grad(z, boxes, rgb), base.edit_steps(z, boxes, rgb, n_steps=3))
+            for other in (pdl, seq):
+                for rep in range(2):
+                    got = (other.reconstruct(x, return_z=True), other.grad(z, boxes, rgb), other.edit_steps(z, boxes, rgb, n_steps=3))
+                    assert np.array_equal(ref[0][0], got[0][0]) and np.array_equal(ref[0][1], got[0][1]), (n, rep)
+                    assert np.array_equal(ref[1], got[1]) and np.array_equal(ref[2], got[2]), (n, rep)
+    finally:
+        base.close()
+        pdl.close()
+        seq.close()
