@@ -174,7 +174,7 @@ struct ian_handle {
   bool tc2 = true;             // CTA-pair tap-GEMM for layers with enough whole tiles (IAN_TC2=0 turns it off)
   bool coop_finalize = true;   // deep split-K layers: cooperative finalize kernel (IAN_FINALIZE8=0: one thread per output everywhere)
   bool pdl = true;             // programmatic dependent launch along the kernel chains (tapgemm.h; IAN_PDL=0 turns it off)
-  bool tc2_splitk = false;     // float32 mode: deep-K layers with few tiles split K over the SM pairs in the pair kernel (IAN_TC2_SPLITK=1)
+  bool tc2_splitk = true;      // float32 mode: deep-K layers with few tiles split K over the SM pairs in the pair kernel (IAN_TC2_SPLITK=0)
   bool tc2_over_split = true;  // float32 mode: the pair kernel (un-split, stream-K) also takes layers choose_ksplit() would split (IAN_TC2_OVER_SPLIT=0)
   int tc2_min_tiles = 37;      // pair-tiles needed before a layer moves to the pair kernel (IAN_TC2_MIN); half a wave: stream-K fills it
   std::string tc2_skip;        // comma-separated layer names kept on the one-CTA kernel (IAN_TC2_SKIP)
