@@ -9,7 +9,7 @@ tail -2 gpurun_out/ncu_f.log | cut -c1-300
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_edit_b128.csv python tools/edit_once.py > /dev/null 2>&1
 FULL_PREC=bf16 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_full_ian_bf16_b512.csv python tools/full_once.py > /dev/null 2>&1
 # --set full of the full-IAN bf16 tensor-core kernels (second iteration): what bounds the Cout = 128 layers
-FULL_PREC=bf16 FULL_IT=2 timeout 900 ncu --set full --clock-control none -k regex:'tapgemm_tc|head_tc|conv1_tc' -s 18 -c 18 -o gpurun_out/r2_prof_full python tools/full_once.py > gpurun_out/ncu_full.log 2>&1
+[ -z "$SKIP_FULL_NCU" ] && FULL_PREC=bf16 FULL_IT=2 timeout 900 ncu --set full --clock-control none -k regex:'tapgemm_tc|head_tc|conv1_tc' -s 18 -c 18 -o gpurun_out/r2_prof_full python tools/full_once.py > gpurun_out/ncu_full.log 2>&1
 # sanitizer: small batches through every kernel family (forward, brush, edit, full IAN, v1)
 cat > /tmp/san.py <<'PY'
 import importlib, sys, numpy as np
@@ -25,6 +25,10 @@ for n in (1, 5):
     m.grad(z, boxes, rgb); m.edit_steps(z, boxes, rgb, n_steps=2)
 x = rng.uniform(-1, 1, (160, 3, 64, 64)).astype(np.float32)      # large enough for the pair kernel and stream-K
 m.reconstruct(x)
+x = rng.uniform(-1, 1, (256, 3, 64, 64)).astype(np.float32)      # enc_fc1 on the pair kernel's split-K
+m.reconstruct(x)
+z, boxes, rgb = ow.config4_inputs(128)                            # the batch-128 edit step: seed kernel, pair stream-K backward, cooperative finalize
+m.edit_steps(z, boxes, rgb, n_steps=2)
 m.close()
 f = pkg.IAN("IAN.py", True, weights=ow.make_full_weights(0))
 x = rng.uniform(-1, 1, (3, 3, 64, 64)).astype(np.float32)
