@@ -13,7 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "neural-photo-editor_b200", "libian_b200.so")
 PAT = re.compile(r"\b(UTC[A-Z]*MMA(?:\.2CTA)?|LDTM|STTM|UTMALDG(?:\.[0-9]D)?(?:\.2CTA)?|UTMASTG|UBLKCP|UTCBAR(?:\.2CTA)?(?:\.MULTICAST)?|"
-                 r"UTCATOMSWS(?:\.2CTA)?|UCGABAR_[A-Z]+|SYNCS\.[A-Z]+|HMMA|FFMA|MUFU\.[A-Z0-9]+|LDGSTS|RED|ATOM[GS]?)\b")
+                 r"UTCATOMSWS(?:\.2CTA)?|UCGABAR_[A-Z]+|SYNCS\.[A-Z]+|HMMA|FFMA|MUFU\.[A-Z0-9]+|LDGSTS|RED|ATOM[GS]?|"
+                 r"STG\.E\.ENL2\.256|PREEXIT|ACQBULK)\b")   # 256-bit stores; griddepcontrol.launch_dependents / .wait (PDL)
 
 
 def demangle(names):
