@@ -26,7 +26,16 @@
  *     (default: layers with >= IAN_TC2_MIN (37) whole pair-tiles run on CTA pairs, tcgen05 cta_group::2);
  *     IAN_TC2_SKIP=<layer,layer> exempts layers; IAN_TC2_BF16=0 keeps bf16-mode layers off the 256x256 pair tiles;
  *     IAN_SPLITK=0 disables split-K (tests); IAN_PUSH=kernel makes the pipelined all-gather push with a copy kernel
- *     (IAN_PUSH_CTAS=<n> CTAs) instead of copy engines + stream memory operations.
+ *     (IAN_PUSH_CTAS=<n> CTAs) instead of copy engines + stream memory operations; IAN_PDL=0 launches the kernel chains
+ *     plainly instead of with programmatic dependent launch; IAN_TC2_SPLITK=0 / IAN_TC2_OVER_SPLIT=0 / IAN_FINALIZE8=0 choose
+ *     the older split-K forms.  All of these select schedules or launch forms of the same kernels;
+ *     results do not depend on IAN_GRAPHS, IAN_PDL or IAN_FINALIZE8 (bit-identical), the others change float32 summation
+ *     order within the tolerances of the parity tests.
+ *   - stream semantics of *_dev calls: kernels of one call are chained with programmatic dependent launch among themselves;
+ *     towards the caller's own work on `stream` (kernels, copies, events before and after the call) the usual stream order
+ *     holds -- the first kernel of a call waits for everything enqueued before it before it reads or writes any argument,
+ *     and a kernel the caller launches afterwards without the programmatic attribute starts after the call's last kernel
+ *     has completed.
  */
 #ifndef IAN_B200_H_
 #define IAN_B200_H_
