@@ -239,8 +239,8 @@ def main():
     ap.add_argument("--no-full", action="store_true", help="skip the full-IAN (BASELINE configs[2]) block")
     ap.add_argument("--no-config5", action="store_true", help="skip the global-batch-4096 block (BASELINE configs[4])")
     ap.add_argument("--gather", default="p2p_async", choices=["p2p_async", "p2p", "nccl"],
-                    help="N>1: p2p_async = decoded shard pushed to the peers by a side-stream copy kernel while the next step "
-                         "computes (default); p2p = peer stores fused into the dec_out kernel; nccl = separate NCCL all_gather")
+                    help="N>1: p2p_async = decoded shard pushed to the peers on a side stream (copy engines + stream memory "
+                         "operations; IAN_PUSH=kernel: a copy kernel) while the next step computes (default); p2p = peer stores fused into the dec_out kernel; nccl = separate NCCL all_gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -571,8 +571,8 @@ def main():
                            "collective": {"none": "none", "nccl": "NCCL all_gather of decoded images after dec_out",
                                           "p2p": "all-gather fused into dec_out: st.global to every rank's buffer over NVLink "
                                                  "peer memory + flag barrier",
-                                          "p2p_async": "all-gather by the library's own side-stream copy kernel over NVLink peer memory "
-                                                       "(free/pushed flag handshake), overlapped with the next step's tensor kernels; "
+                                          "p2p_async": "all-gather by the library's own side-stream push over NVLink peer memory (copy engines + "
+                                                       "stream memory operations unless IAN_PUSH=kernel; free/pushed flag handshake), overlapped with the next step's tensor kernels; "
                                                        "the last step's gather completes inside the timed region"}[gather_mode],
                            "gather_check_max_abs_vs_nccl": gather_check},
                 "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

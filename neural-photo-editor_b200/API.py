@@ -444,8 +444,8 @@ class IAN:
         return out.value
 
     def reconstruct_gather_async_dev(self, x_ptr, n_local, z_ptr=0, stream=0):
-        """pipelined form: enqueue this rank's shard; a side-stream copy kernel pushes it to the peers while the next
-        call computes.  gather_wait_dev() returns the complete buffer of the most recent step."""
+        """pipelined form: enqueue this rank's shard; a side stream pushes it to the peers (copy engines + stream memory
+        operations; IAN_PUSH=kernel: a copy kernel) while the next call computes.  gather_wait_dev() returns the complete buffer of the most recent step."""
         self._check(self._lib.ian_reconstruct_gather_async_dev(self._h, x_ptr, int(n_local), z_ptr or None, stream or None))
 
     def gather_wait_dev(self, stream=0):
