@@ -175,14 +175,17 @@ def test_simple_model_function_set_is_flowless(model, golden):
 
 def test_bf16_mode_tolerance_vs_oracle(full_model, gold):
     """BASELINE configs[2]: full IAN in bf16 with an fp32 tolerance check.  Operands rounded to bf16 (8 significand
-    bits), fp32 accumulation.  Measured on [-1,1] images: max-abs 0.10 (the Beta ratio 2a/(a+b) is steep where both
-    sigmoids are small), mean-abs 3.1e-3.  Bounds stated here: max-abs 0.2, mean-abs 8e-3."""
+    bits), fp32 accumulation.  Measured on this fixture's [-1,1] images (final round-2 build; the kernels are
+    deterministic, so every B200 gives these bits): max-abs 0.034 (the Beta ratio 2a/(a+b) is steep where both sigmoids
+    are small), mean-abs 2.6e-3.  Bounds stated here: max-abs 0.08, mean-abs 5e-3 (bench.py reports max-abs / mean-abs /
+    PSNR of bf16 vs float32 mode at batch 512: 0.065 / 2.8e-3 / 52.7 dB)."""
     x = on.to_tanh(gold["images"].astype(np.float64)).astype(np.float32)
     try:
         full_model.set_precision("bf16")
         xh = full_model.sample_at(gold["z_rand"])
         err = np.abs(xh - gold["xhat_rand"])
-        assert err.max() <= 0.2 and err.mean() <= 8e-3, (err.max(), err.mean())
+        print("bf16 vs oracle: max-abs %.4f mean-abs %.5f" % (err.max(), err.mean()))
+        assert err.max() <= 0.08 and err.mean() <= 5e-3, (err.max(), err.mean())
         z = full_model.encode_images(x)
         assert (np.abs(z - gold["z"]) <= 6e-2 * (1.0 + np.abs(gold["z"]))).all()
         # the fp32 verification path run on the same bf16-rounded operands agrees to about the same level (bf16 re-rounding of activations amplifies 1-ulp differences)
@@ -222,7 +225,8 @@ def test_ianv1_golden(npe, gold_v1, path):
         if path == "tc":
             m.set_precision("bf16")
             err = np.abs(m.sample_at(gold_v1["z_rand"]) - gold_v1["xhat_rand"])
-            assert err.max() <= 0.2 and err.mean() <= 8e-3
+            print("IANv1 bf16 vs oracle: max-abs %.4f mean-abs %.5f" % (err.max(), err.mean()))
+            assert err.max() <= 0.03 and err.mean() <= 3e-3     # measured 0.0061 / 7.5e-4 (plain deconv decoder: no steep MDC/Beta chain)
     finally:
         m.close()
 
