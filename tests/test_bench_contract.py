@@ -38,3 +38,21 @@ def test_reference_arm_nonzero_ranks_do_no_work():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_roofline_traffic_resolves_from_the_committed_ncu_summary():
+    """`roofline.traffic` is read at run time from profiles/r2_ncu_tc_kernels_full_summary.csv (the ncu --set full capture of
+    the same command), not a constant in the source: the 9 tap-GEMM launches of one batch-256 step must all be there, their
+    DRAM bytes between the algorithmic 0.94 GB and 2x that, and the bench line committed beside it must carry that figure."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    t = bench.ncu_traffic("tapgemm_tc", 9)
+    assert t is not None and 0.94e9 <= t <= 1.9e9, t
+    assert bench.ncu_traffic("tapgemm_tc", 10) is None           # a step has exactly nine of them: more cannot be resolved
+    line = [l for l in open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")) if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert abs(d["roofline"]["traffic"] - t) <= 0.1 * t          # (that line was printed just before the capture was refreshed in the same call)
+    assert d["roofline"]["traffic_src"].endswith("r2_ncu_tc_kernels_full_summary.csv")
+    assert d["roofline"]["frac"] == d["roofline"]["frac_burst"] and 0.5 < d["roofline"]["frac_burst"] <= 1.0
+    assert d["gpu_launches"] == 14 * d["steps"]                  # conv1, 3 convs, fc1 + finalize, head + finalize, sample, fc2, 3 deconvs, dec_out
